@@ -1,0 +1,13 @@
+"""blenderraytracer_b200 — B200-native (sm_100a) drop-in for the render path of Shinzef/BlenderRayTracer.
+
+Only what the hot path needs lives here: ``csrc/`` (hand-written CUDA kernels + the C ABI of include/brt.h, built
+into ``libbrt.so``) and the host-side mirror of the reference's ``RayTracer`` / scene classes.  Importing the package
+does not touch the GPU; constructing a ``RayTracer`` does, and fails loudly without one (no CPU fallback).
+"""
+from ._lib import BrtError, LIB_PATH, load  # noqa: F401
+from .raytracer import RayTracer, make_perm  # noqa: F401
+from .scene import (Box, Dielectric, DirectionalLight, Emissive, Lambertian, Metal, Plane, PointLight, Sphere,  # noqa: F401
+                    Triangle, TriangleMesh, World)
+
+__all__ = ["RayTracer", "World", "Sphere", "Plane", "Box", "Triangle", "TriangleMesh", "Lambertian", "Metal", "Dielectric",
+           "Emissive", "PointLight", "DirectionalLight", "BrtError", "make_perm", "load", "LIB_PATH"]

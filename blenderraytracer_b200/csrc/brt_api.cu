@@ -1,0 +1,711 @@
+// C ABI of libbrt (include/brt.h): context, scene upload (SoA flattening), LBVH build, render orchestration.
+// Replaces RayTracer.render() (reference js/ray-tracer.js:166-281).  No CPU fallback exists: every compute entry
+// point needs a CUDA device.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "brt_host.hpp"
+#include "brt_kernels.h"
+
+using namespace brt;
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes ? bytes : 16;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct brt_ctx {
+    int device = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    std::string err;
+    HostScene scene; bool haveScene = false;
+    HostBackground bg;
+    brt_camera cam{}; bool haveCam = false;
+    brt_render_params rp{};
+    // device scene
+    DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm;
+    float4* dNodes = nullptr;
+    DevScene dev{};
+    bool sceneDirty = true, permDirty = true;
+    int nBounded = 0;
+    brt_scene_info info{};
+    // frame buffers
+    DevBuf dAccum, dRgba, dFloat, dFloat2, dLinear, dCounters, dScratch;
+    // fp64 parity data (lazy)
+    DevBuf dObj64, dTris64; bool obj64Dirty = true;
+    std::atomic<int> cancel{ 0 };
+    brt_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+};
+
+static int fail(brt_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+static int cuda_fail(brt_ctx* c, cudaError_t e, const char* where) {
+    return fail(c, BRT_E_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define NEED_GPU() do { if (ctx->device < 0) return fail(ctx, BRT_E_CUDA, "host-only context (device_id = -1): no GPU, and libbrt has no CPU fallback"); } while (0)
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+static void default_params(brt_render_params& p) {                 // ray-tracer.js:19-30
+    memset(&p, 0, sizeof(p));
+    p.width = 600; p.height = 400; p.spp = 4; p.max_depth = 5; p.aa_mode = BRT_AA_SUPERSAMPLING; p.tonemap = BRT_TONEMAP_REINHARD;
+    p.exposure = 1.0; p.gamma = 2.2; p.denoise = 0; p.denoise_strength = 0.5; p.seed = 1;
+}
+static void identity_perm(uint8_t* perm) { for (int i = 0; i < 512; i++) perm[i] = (uint8_t)(i & 255); }
+
+extern "C" {
+
+int brt_abi_version(void) { return BRT_ABI_VERSION; }
+const char* brt_version(void) { return "libbrt 0.1 (sm_100a)"; }
+
+int brt_create(brt_ctx** out, int device_id) {
+    if (!out) return BRT_E_INVALID;
+    *out = nullptr;
+    if (device_id == -1) {
+        // host-only context: scene ingest / camera / parameter logic without a device (used by CPU-side tests and
+        // tooling).  Every compute entry point on such a context fails with BRT_E_CUDA — there is no CPU renderer.
+        brt_ctx* h = new (std::nothrow) brt_ctx();
+        if (!h) return BRT_E_NOMEM;
+        h->device = -1;
+        default_params(h->rp);
+        identity_perm(h->bg.perm);
+        *out = h;
+        return BRT_OK;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return BRT_E_CUDA;             // no CPU fallback, by design
+    if (device_id < 0 || device_id >= n) return BRT_E_INVALID;
+    if (cudaSetDevice(device_id) != cudaSuccess) return BRT_E_CUDA;
+    brt_ctx* ctx = new (std::nothrow) brt_ctx();
+    if (!ctx) return BRT_E_NOMEM;
+    ctx->device = device_id;
+    default_params(ctx->rp);
+    identity_perm(ctx->bg.perm);
+    if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BRT_E_CUDA; }
+    ctx->stream = ctx->ownStream;
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2);
+    *out = ctx;
+    return BRT_OK;
+}
+
+void brt_destroy(brt_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->device < 0) { delete ctx; return; }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = { &ctx->dSph, &ctx->dPln, &ctx->dBox, &ctx->dTri, &ctx->dMeta, &ctx->dMat, &ctx->dMatType, &ctx->dLights, &ctx->dPerm,
+                       &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch,
+                       &ctx->dObj64, &ctx->dTris64 };
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->dNodes) cudaFree(ctx->dNodes);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+}
+
+const char* brt_last_error(const brt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int brt_set_stream(brt_ctx* ctx, void* s) {
+    if (!ctx) return BRT_E_INVALID;
+    NEED_GPU();
+    ctx->stream = s ? (cudaStream_t)s : ctx->ownStream;
+    return BRT_OK;
+}
+int brt_stream_synchronize(brt_ctx* ctx) {
+    if (!ctx) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------- scene
+static int validate_scene(brt_ctx* ctx, const HostScene& s) {
+    for (size_t i = 0; i < s.objects.size(); i++) {
+        const brt_object& o = s.objects[i];
+        if (o.type < BRT_OBJ_SPHERE || o.type > BRT_OBJ_MESH) return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": bad type");
+        if (o.material < 0 || (size_t)o.material >= s.materials.size()) return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": bad material index");
+        if (o.type == BRT_OBJ_MESH) {
+            if (o.first_tri < 0 || o.tri_count < 0 || (size_t)(o.first_tri + o.tri_count) * 9 > s.meshTris.size())
+                return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": mesh triangle range out of bounds");
+        }
+    }
+    for (const brt_material& m : s.materials) if (m.type < 0 || m.type > 3) return fail(ctx, BRT_E_INVALID, "bad material type");
+    for (const brt_light& l : s.lights) if (l.type < 0 || l.type > 1) return fail(ctx, BRT_E_INVALID, "bad light type");
+    return BRT_OK;
+}
+
+int brt_scene_load_json(brt_ctx* ctx, const char* utf8, size_t len, int fw, int fh, int* out_has_camera, int* out_w, int* out_h) {
+    if (!ctx || !utf8) return BRT_E_INVALID;
+    if (fw <= 0 || fh <= 0) return fail(ctx, BRT_E_INVALID, "fallback width/height must be positive");
+    HostScene sc; bool hasCam = false; int w = 0, h = 0; std::string err;
+    brt_camera cam = ctx->cam; HostBackground bg = ctx->bg;
+    int rc = load_scene_json(utf8, len, fw, fh, sc, bg, cam, hasCam, w, h, err);
+    if (rc != BRT_OK) return fail(ctx, rc, err);
+    if ((rc = validate_scene(ctx, sc)) != BRT_OK) return rc;
+    ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true;
+    ctx->bg = bg;
+    if (hasCam) { ctx->cam = cam; ctx->haveCam = true; }           // ray-tracer.js:315-317
+    if (out_has_camera) *out_has_camera = hasCam ? 1 : 0;
+    if (out_w) *out_w = w;
+    if (out_h) *out_h = h;
+    return BRT_OK;
+}
+
+int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {
+    if (!ctx || !d) return BRT_E_INVALID;
+    if (d->n_objects < 0 || d->n_materials < 0 || d->n_lights < 0 || d->n_mesh_triangles < 0) return fail(ctx, BRT_E_INVALID, "negative count");
+    if ((d->n_objects && !d->objects) || (d->n_materials && !d->materials) || (d->n_lights && !d->lights) || (d->n_mesh_triangles && !d->mesh_triangles))
+        return fail(ctx, BRT_E_INVALID, "null array with non-zero count");
+    HostScene sc;
+    sc.objects.assign(d->objects, d->objects + d->n_objects);
+    sc.materials.assign(d->materials, d->materials + d->n_materials);
+    sc.lights.assign(d->lights, d->lights + d->n_lights);
+    sc.meshTris.assign(d->mesh_triangles, d->mesh_triangles + 9 * (size_t)d->n_mesh_triangles);
+    for (brt_object& o : sc.objects) if (o.type == BRT_OBJ_PLANE) {               // geometry.js:52
+        double l = std::sqrt(o.b[0] * o.b[0] + o.b[1] * o.b[1] + o.b[2] * o.b[2]);
+        if (l > 0) { o.b[0] /= l; o.b[1] /= l; o.b[2] /= l; } else o.b[0] = o.b[1] = o.b[2] = 0;
+    }
+    for (brt_material& m : sc.materials) if (m.type == BRT_MAT_METAL && !(m.param != m.param)) m.param = std::fmin(m.param, 1.0);   // materials.js:33
+    for (brt_light& l : sc.lights) if (l.type == BRT_LIGHT_DIRECTIONAL) {         // lights.js:38
+        double n = std::sqrt(l.v[0] * l.v[0] + l.v[1] * l.v[1] + l.v[2] * l.v[2]);
+        if (n > 0) { l.v[0] /= n; l.v[1] /= n; l.v[2] /= n; } else l.v[0] = l.v[1] = l.v[2] = 0;
+    }
+    int rc = validate_scene(ctx, sc);
+    if (rc != BRT_OK) return rc;
+    ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true;
+    return BRT_OK;
+}
+
+static float4 f4(double x, double y, double z, double w) { return make_float4((float)x, (float)y, (float)z, (float)w); }
+
+// Flatten world.objects into per-type SoA float4 arrays + unified meta, upload, build the LBVH.
+static int upload_scene(brt_ctx* ctx) {
+    NEED_GPU();
+    if (!ctx->sceneDirty) return BRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    auto t0 = std::chrono::steady_clock::now();
+    const HostScene& s = ctx->scene;
+    std::vector<float4> sph, pln, box, tri, mat, lights;
+    std::vector<int4> mSph, mPln, mBox, mTri;
+    std::vector<int> matType;
+    size_t nTriTotal = 0;
+    for (const brt_object& o : s.objects) nTriTotal += o.type == BRT_OBJ_TRIANGLE ? 1 : o.type == BRT_OBJ_MESH ? (size_t)o.tri_count : 0;
+    if (nTriTotal >= (1u << 28) || s.objects.size() >= (1u << 28)) return fail(ctx, BRT_E_INVALID, "too many primitives (limit 2^28 per type)");
+    tri.reserve(3 * nTriTotal); mTri.reserve(nTriTotal);
+    auto push_tri = [&](const double* v0, const double* v1, const double* v2, int obj, int m, int triId) {
+        tri.push_back(f4(v0[0], v0[1], v0[2], 0));
+        // edges are formed in float64 and rounded once (geometry.js:150-151 recomputes them per hit in float64)
+        tri.push_back(f4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], 0));
+        tri.push_back(f4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0));
+        mTri.push_back(make_int4(obj, m, triId, 0));
+    };
+    for (size_t i = 0; i < s.objects.size(); i++) {
+        const brt_object& o = s.objects[i];
+        int obj = (int)i;
+        switch (o.type) {
+        case BRT_OBJ_SPHERE: sph.push_back(f4(o.a[0], o.a[1], o.a[2], o.b[0])); mSph.push_back(make_int4(obj, o.material, -1, 0)); break;
+        case BRT_OBJ_PLANE: pln.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); pln.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); mPln.push_back(make_int4(obj, o.material, -1, 0)); break;
+        case BRT_OBJ_BOX: box.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); box.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); mBox.push_back(make_int4(obj, o.material, -1, 0)); break;
+        case BRT_OBJ_TRIANGLE: push_tri(o.a, o.b, o.c, obj, o.material, -1); break;
+        default:
+            for (int64_t t = 0; t < o.tri_count; t++) {
+                const double* p = &s.meshTris[9 * (size_t)(o.first_tri + t)];
+                push_tri(p, p + 3, p + 6, obj, o.material, (int)t);
+            }
+        }
+    }
+    for (const brt_material& m : s.materials) { mat.push_back(f4(m.color[0], m.color[1], m.color[2], m.param)); matType.push_back(m.type); }
+    for (const brt_light& l : s.lights) {
+        lights.push_back(f4(l.v[0], l.v[1], l.v[2], l.type == BRT_LIGHT_DIRECTIONAL ? 1.0 : 0.0));
+        lights.push_back(f4(l.color[0] * l.intensity, l.color[1] * l.intensity, l.color[2] * l.intensity, 0));
+    }
+    std::vector<int4> meta;
+    DevScene& d = ctx->dev;
+    d.baseSph = 0; meta.insert(meta.end(), mSph.begin(), mSph.end());
+    d.basePln = (int)meta.size(); meta.insert(meta.end(), mPln.begin(), mPln.end());
+    d.baseBox = (int)meta.size(); meta.insert(meta.end(), mBox.begin(), mBox.end());
+    d.baseTri = (int)meta.size(); meta.insert(meta.end(), mTri.begin(), mTri.end());
+    d.nSph = (int)mSph.size(); d.nPln = (int)mPln.size(); d.nBox = (int)mBox.size(); d.nTri = (int)mTri.size();
+    d.nLights = (int)s.lights.size();
+    auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = b.ensure(bytes);
+        if (e != cudaSuccess) return e;
+        if (bytes) e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        return e;
+    };
+    CK(up(ctx->dSph, sph.data(), sph.size() * sizeof(float4)));
+    CK(up(ctx->dPln, pln.data(), pln.size() * sizeof(float4)));
+    CK(up(ctx->dBox, box.data(), box.size() * sizeof(float4)));
+    CK(up(ctx->dTri, tri.data(), tri.size() * sizeof(float4)));
+    CK(up(ctx->dMeta, meta.data(), meta.size() * sizeof(int4)));
+    CK(up(ctx->dMat, mat.data(), mat.size() * sizeof(float4)));
+    CK(up(ctx->dMatType, matType.data(), matType.size() * sizeof(int)));
+    CK(up(ctx->dLights, lights.data(), lights.size() * sizeof(float4)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    d.sph = (const float4*)ctx->dSph.p; d.pln = (const float4*)ctx->dPln.p; d.box = (const float4*)ctx->dBox.p; d.tri = (const float4*)ctx->dTri.p;
+    d.meta = (const int4*)ctx->dMeta.p; d.mat = (const float4*)ctx->dMat.p; d.matType = (const int*)ctx->dMatType.p;
+    d.lights = (const float4*)ctx->dLights.p;
+    auto t1 = std::chrono::steady_clock::now();
+    // LBVH over the bounded primitives
+    if (ctx->dNodes) { cudaFree(ctx->dNodes); ctx->dNodes = nullptr; }
+    d.nodes = nullptr; d.nNodes = 0;
+    ctx->nBounded = d.nSph + d.nBox + d.nTri;
+    BvhBuildResult br{};
+    CK(build_lbvh(d, &br, ctx->stream));
+    if (br.depth > SMEM_STACK + LOCAL_STACK) {
+        if (br.nodes) cudaFree(br.nodes);
+        return fail(ctx, BRT_E_STATE, "LBVH deeper than the traversal stack (" + std::to_string(br.depth) + ")");
+    }
+    ctx->dNodes = br.nodes; d.nodes = br.nodes; d.nNodes = (int)br.nNodes; d.bvhStackDepth = br.depth;
+    brt_scene_info& inf = ctx->info;
+    inf.n_objects = (int)s.objects.size(); inf.n_materials = (int)s.materials.size(); inf.n_lights = (int)s.lights.size();
+    inf.n_spheres = d.nSph; inf.n_planes = d.nPln; inf.n_boxes = d.nBox; inf.n_triangles = d.nTri;
+    inf.n_bvh_nodes = br.nNodes; inf.bvh_depth = br.depth; inf.bvh_build_ms = br.buildMs;
+    inf.upload_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    ctx->sceneDirty = false;
+    return BRT_OK;
+}
+
+static int upload_perm(brt_ctx* ctx) {
+    NEED_GPU();
+    if (!ctx->permDirty && ctx->dPerm.p) { ctx->dev.perm = (const unsigned char*)ctx->dPerm.p; return BRT_OK; }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->dPerm.ensure(512));
+    CK(cudaMemcpyAsync(ctx->dPerm.p, ctx->bg.perm, 512, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dev.perm = (const unsigned char*)ctx->dPerm.p;
+    ctx->permDirty = false;
+    return BRT_OK;
+}
+
+int brt_scene_info_get(brt_ctx* ctx, brt_scene_info* out) {
+    if (!ctx || !out) return BRT_E_INVALID;
+    if (!ctx->haveScene) return fail(ctx, BRT_E_NOSCENE, "no scene loaded");
+    if (ctx->device < 0) {
+        memset(out, 0, sizeof(*out));
+        const HostScene& s = ctx->scene;
+        out->n_objects = (int)s.objects.size(); out->n_materials = (int)s.materials.size(); out->n_lights = (int)s.lights.size();
+        for (const brt_object& o : s.objects) {
+            if (o.type == BRT_OBJ_SPHERE) out->n_spheres++; else if (o.type == BRT_OBJ_PLANE) out->n_planes++;
+            else if (o.type == BRT_OBJ_BOX) out->n_boxes++; else if (o.type == BRT_OBJ_TRIANGLE) out->n_triangles++;
+            else out->n_triangles += o.tri_count;
+        }
+        return BRT_OK;
+    }
+    int rc = upload_scene(ctx);
+    if (rc != BRT_OK) return rc;
+    *out = ctx->info;
+    return BRT_OK;
+}
+int brt_scene_get_flat(brt_ctx* ctx, brt_scene_desc* out) {
+    if (!ctx || !out) return BRT_E_INVALID;
+    if (!ctx->haveScene) return fail(ctx, BRT_E_NOSCENE, "no scene loaded");
+    const HostScene& s = ctx->scene;
+    memset(out, 0, sizeof(*out));
+    out->objects = s.objects.data(); out->n_objects = (int)s.objects.size();
+    out->materials = s.materials.data(); out->n_materials = (int)s.materials.size();
+    out->mesh_triangles = s.meshTris.data(); out->n_mesh_triangles = (int64_t)(s.meshTris.size() / 9);
+    out->lights = s.lights.data(); out->n_lights = (int)s.lights.size();
+    return BRT_OK;
+}
+
+int brt_set_camera(brt_ctx* ctx, const brt_camera* cam) {
+    if (!ctx || !cam) return BRT_E_INVALID;
+    if (cam->type < BRT_CAM_PERSPECTIVE || cam->type > BRT_CAM_OTHER) return fail(ctx, BRT_E_INVALID, "bad camera type");
+    ctx->cam = *cam;
+    if (!cam->use_derived) derive_camera(ctx->cam);
+    ctx->haveCam = true;
+    return BRT_OK;
+}
+int brt_get_camera(brt_ctx* ctx, brt_camera* out) {
+    if (!ctx || !out) return BRT_E_INVALID;
+    if (!ctx->haveCam) return fail(ctx, BRT_E_NOSCENE, "no camera set");
+    *out = ctx->cam;
+    return BRT_OK;
+}
+int brt_set_background(brt_ctx* ctx, int kind, const double color[3], double intensity, const uint8_t* perm256) {
+    if (!ctx) return BRT_E_INVALID;
+    if (kind < BRT_BG_GRADIENT || kind > BRT_BG_PROCEDURAL_SKY) return fail(ctx, BRT_E_INVALID, "bad background kind");
+    ctx->bg.kind = kind; ctx->bg.intensity = intensity;
+    if (color) for (int k = 0; k < 3; k++) ctx->bg.color[k] = color[k];
+    if (perm256) { for (int i = 0; i < 512; i++) ctx->bg.perm[i] = perm256[i & 255]; ctx->permDirty = true; }   // noise.js:16-17
+    return BRT_OK;
+}
+int brt_get_background(brt_ctx* ctx, int* kind, double color[3], double* intensity) {
+    if (!ctx) return BRT_E_INVALID;
+    if (kind) *kind = ctx->bg.kind;
+    if (color) for (int k = 0; k < 3; k++) color[k] = ctx->bg.color[k];
+    if (intensity) *intensity = ctx->bg.intensity;
+    return BRT_OK;
+}
+int brt_set_render_params(brt_ctx* ctx, const brt_render_params* p) {
+    if (!ctx || !p) return BRT_E_INVALID;
+    if (p->width < 1 || p->height < 1 || p->width > 65536 || p->height > 65536) return fail(ctx, BRT_E_INVALID, "bad image size");
+    if (p->spp < 1) return fail(ctx, BRT_E_INVALID, "spp must be >= 1");
+    if (p->max_depth < 0) return fail(ctx, BRT_E_INVALID, "max_depth must be >= 0");
+    if (p->aa_mode < 0 || p->aa_mode > 3 || p->tonemap < 0 || p->tonemap > 2) return fail(ctx, BRT_E_INVALID, "bad aa_mode / tonemap");
+    if (p->sampler < 0 || p->sampler > 1 || p->integrator < 0 || p->integrator > 2 || p->accel < 0 || p->accel > 2)
+        return fail(ctx, BRT_E_INVALID, "bad sampler / integrator / accel");
+    ctx->rp = *p;
+    return BRT_OK;
+}
+int brt_get_render_params(brt_ctx* ctx, brt_render_params* out) {
+    if (!ctx || !out) return BRT_E_INVALID;
+    *out = ctx->rp;
+    return BRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------- render
+static bool use_bvh(const brt_ctx* ctx) {
+    if (ctx->dev.nNodes == 0) return false;
+    if (ctx->rp.accel == BRT_ACCEL_BRUTE) return false;
+    if (ctx->rp.accel == BRT_ACCEL_BVH) return true;
+    return ctx->nBounded >= 8;
+}
+static int effective_spp(const brt_render_params& rp) { return rp.aa_mode == BRT_AA_NONE ? 1 : rp.spp; }    // ray-tracer.js:201
+
+static int prepare(brt_ctx* ctx, PTParams& p) {
+    NEED_GPU();
+    if (!ctx->haveScene) return fail(ctx, BRT_E_NOSCENE, "no scene loaded");
+    if (!ctx->haveCam) return fail(ctx, BRT_E_NOSCENE, "no camera set");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_scene(ctx);
+    if (rc != BRT_OK) return rc;
+    if ((rc = upload_perm(ctx)) != BRT_OK) return rc;
+    const brt_render_params& rp = ctx->rp;
+    memset(&p, 0, sizeof(p));
+    ctx->dev.bgKind = ctx->bg.kind; ctx->dev.bgR = (float)ctx->bg.color[0]; ctx->dev.bgG = (float)ctx->bg.color[1];
+    ctx->dev.bgB = (float)ctx->bg.color[2]; ctx->dev.skyIntensity = (float)ctx->bg.intensity;
+    p.sc = ctx->dev;
+    const brt_camera& c = ctx->cam;
+    DevCamera& dc = p.cam;
+    dc.ox = (float)c.origin[0]; dc.oy = (float)c.origin[1]; dc.oz = (float)c.origin[2];
+    dc.llx = (float)c.lower_left_corner[0]; dc.lly = (float)c.lower_left_corner[1]; dc.llz = (float)c.lower_left_corner[2];
+    dc.hx = (float)c.horizontal[0]; dc.hy = (float)c.horizontal[1]; dc.hz = (float)c.horizontal[2];
+    dc.vx = (float)c.vertical[0]; dc.vy = (float)c.vertical[1]; dc.vz = (float)c.vertical[2];
+    dc.ux = (float)c.u[0]; dc.uy = (float)c.u[1]; dc.uz = (float)c.u[2];
+    dc.wx = (float)c.w[0]; dc.wy = (float)c.w[1]; dc.wz = (float)c.w[2];
+    dc.vvx = (float)c.v[0]; dc.vvy = (float)c.v[1]; dc.vvz = (float)c.v[2];
+    dc.lensRadius = (float)c.lens_radius; dc.type = c.type;
+    p.W = rp.width; p.H = rp.height; p.maxDepth = rp.max_depth; p.aaMode = rp.aa_mode;
+    p.seedLo = (uint32_t)rp.seed; p.seedHi = (uint32_t)(rp.seed >> 32);
+    p.directLighting = rp.direct_lighting ? 1 : 0;
+    return BRT_OK;
+}
+
+static int z_split(const brt_ctx* ctx, int samplesInLaunch) {
+    // keep >= ~4 resident waves of threads on 148 SMs when the image is small (then atomics merge the chunks)
+    const long long want = 148LL * 2048 * 2;
+    long long px = (long long)ctx->rp.width * ctx->rp.height;
+    if (px >= want || samplesInLaunch < 2) return 1;
+    long long z = (want + px - 1) / px;
+    if (z > samplesInLaunch) z = samplesInLaunch;
+    if (z > 64) z = 64;
+    return (int)z;
+}
+
+static int launch_samples(brt_ctx* ctx, PTParams& p, float* dAccum, int sBegin, int sCount) {
+    p.accum = (float4*)dAccum; p.sBegin = sBegin; p.sCount = sCount;
+    const bool count = ctx->rp.count_tests != 0;
+    if (count) {
+        CK(ctx->dCounters.ensure(8 * sizeof(unsigned long long)));
+        p.counters = (unsigned long long*)ctx->dCounters.p;
+    }
+    if (p.maxDepth <= 0) return BRT_OK;                             // rayColor(depth <= 0) is black (ray-tracer.js:103)
+    CK(launch_pathtrace(p, ctx->rp.sampler, use_bvh(ctx), count, z_split(ctx, sCount), ctx->stream));
+    ctx->stats.launches++;
+    return BRT_OK;
+}
+
+static PostParams post_params(const brt_ctx* ctx) {
+    PostParams pp{};
+    pp.W = ctx->rp.width; pp.H = ctx->rp.height; pp.tonemap = ctx->rp.tonemap; pp.exposure = ctx->rp.exposure;
+    pp.invGamma = 1.0 / ctx->rp.gamma;                              // post-processor.js:36
+    double s = ctx->rp.denoise_strength;
+    pp.w1 = std::exp(-1.0 / (2 * s * s)); pp.w2 = std::exp(-2.0 / (2 * s * s));   // post-processor.js:59
+    return pp;
+}
+
+int brt_render_accumulate(brt_ctx* ctx, float* d_accum, int sample_begin, int sample_count) {
+    if (!ctx) return BRT_E_INVALID;
+    if (sample_begin < 0 || sample_count < 0) return fail(ctx, BRT_E_INVALID, "negative sample range");
+    PTParams p;
+    int rc = prepare(ctx, p);
+    if (rc != BRT_OK) return rc;
+    size_t px = (size_t)ctx->rp.width * ctx->rp.height;
+    if (!d_accum) {
+        bool fresh = ctx->dAccum.cap < px * 16;
+        CK(ctx->dAccum.ensure(px * 16));
+        if (fresh) CK(cudaMemsetAsync(ctx->dAccum.p, 0, px * 16, ctx->stream));
+        d_accum = (float*)ctx->dAccum.p;
+    }
+    if (ctx->rp.count_tests) { CK(ctx->dCounters.ensure(64)); CK(cudaMemsetAsync(ctx->dCounters.p, 0, 64, ctx->stream)); }
+    ctx->stats.launches = 0;
+    if (sample_count == 0) return BRT_OK;
+    if ((rc = launch_samples(ctx, p, d_accum, sample_begin, sample_count)) != BRT_OK) return rc;
+    ctx->stats.samples = (uint64_t)px * (uint64_t)sample_count;
+    return BRT_OK;
+}
+
+int brt_resolve_device(brt_ctx* ctx, const float* d_accum, uint8_t* d_rgba8, float* d_float_data, float* d_linear_mean) {
+    if (!ctx) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    size_t px = (size_t)ctx->rp.width * ctx->rp.height;
+    if (!d_accum) d_accum = (const float*)ctx->dAccum.p;
+    if (!d_accum) return fail(ctx, BRT_E_STATE, "no accumulation buffer");
+    PostParams pp = post_params(ctx);
+    if (ctx->rp.denoise) {
+        float4* fd = (float4*)d_float_data;
+        CK(ctx->dFloat2.ensure(px * 16));
+        // denoise reads the un-filtered floatData and (ray-tracer.js:267-275) only the 8-bit image is replaced
+        CK(launch_resolve(pp, (const float4*)d_accum, nullptr, (float4*)ctx->dFloat2.p, (float4*)d_linear_mean, 0, pp.H, ctx->stream));
+        CK(launch_denoise(pp, (const float4*)ctx->dFloat2.p, (uchar4*)d_rgba8, nullptr, ctx->stream));
+        if (fd) CK(cudaMemcpyAsync(fd, ctx->dFloat2.p, px * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->stats.launches += 2;
+    } else {
+        CK(launch_resolve(pp, (const float4*)d_accum, (uchar4*)d_rgba8, (float4*)d_float_data, (float4*)d_linear_mean, 0, pp.H, ctx->stream));
+        ctx->stats.launches += 1;
+    }
+    return BRT_OK;
+}
+
+int brt_reduce_resolve_peers(brt_ctx* ctx, const float* const* d_peer_accum, int n_peers, int row_begin, int row_end,
+                             uint8_t* d_rgba8_root, float* d_float_data_root) {
+    if (!ctx || !d_peer_accum) return BRT_E_INVALID;
+    if (n_peers < 1 || n_peers > 16) return fail(ctx, BRT_E_INVALID, "n_peers must be in [1,16]");
+    NEED_GPU();
+    if (row_begin < 0 || row_end > ctx->rp.height || row_begin > row_end) return fail(ctx, BRT_E_INVALID, "bad row range");
+    CK(cudaSetDevice(ctx->device));
+    PostParams pp = post_params(ctx);
+    CK(launch_reduce_resolve(pp, (const float4* const*)d_peer_accum, n_peers, (uchar4*)d_rgba8_root, (float4*)d_float_data_root,
+                             row_begin, row_end, ctx->stream));
+    ctx->stats.launches += 1;
+    return BRT_OK;
+}
+
+int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_mean, brt_progress_cb cb, void* user) {
+    if (!ctx || !rgba8) return BRT_E_INVALID;
+    auto w0 = std::chrono::steady_clock::now();
+    ctx->cancel.store(0);
+    PTParams p;
+    int rc = prepare(ctx, p);
+    if (rc != BRT_OK) return rc;
+    const size_t px = (size_t)ctx->rp.width * ctx->rp.height;
+    CK(ctx->dAccum.ensure(px * 16)); CK(ctx->dRgba.ensure(px * 4));
+    if (float_data || ctx->rp.denoise) CK(ctx->dFloat.ensure(px * 16));
+    if (linear_mean) CK(ctx->dLinear.ensure(px * 16));
+    CK(cudaMemsetAsync(ctx->dAccum.p, 0, px * 16, ctx->stream));
+    if (ctx->rp.count_tests) { CK(ctx->dCounters.ensure(64)); CK(cudaMemsetAsync(ctx->dCounters.p, 0, 64, ctx->stream)); }
+    ctx->stats = brt_stats{};
+    const int spp = effective_spp(ctx->rp);
+    int batch = ctx->rp.spp_batch > 0 ? ctx->rp.spp_batch : (cb ? (spp + 15) / 16 : spp);
+    if (batch < 1) batch = 1;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int s = 0; s < spp; s += batch) {
+        int n = spp - s < batch ? spp - s : batch;
+        if ((rc = launch_samples(ctx, p, (float*)ctx->dAccum.p, s, n)) != BRT_OK) return rc;
+        if (cb || s + n < spp) {
+            // progress + cooperative cancel between batches (ray-tracer.js:190,256-261)
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->cancel.load()) return fail(ctx, BRT_E_CANCELLED, "render cancelled");
+            if (cb && s + n < spp) cb((double)(s + n) / spp, user);
+        }
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (p.maxDepth <= 0) {
+        // every path is black; alpha must still carry the sample count for the resolve division
+        std::vector<float> z(px * 4, 0.f);
+        for (size_t i = 0; i < px; i++) z[4 * i + 3] = (float)spp;
+        CK(cudaMemcpyAsync(ctx->dAccum.p, z.data(), px * 16, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    rc = brt_resolve_device(ctx, (const float*)ctx->dAccum.p, (uint8_t*)ctx->dRgba.p, (float_data || ctx->rp.denoise) ? (float*)ctx->dFloat.p : nullptr,
+                            linear_mean ? (float*)ctx->dLinear.p : nullptr);
+    if (rc != BRT_OK) return rc;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    CK(cudaMemcpyAsync(rgba8, ctx->dRgba.p, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (float_data) CK(cudaMemcpyAsync(float_data, ctx->dFloat.p, px * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (linear_mean) CK(cudaMemcpyAsync(linear_mean, ctx->dLinear.p, px * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->cancel.load()) return fail(ctx, BRT_E_CANCELLED, "render cancelled");
+    float k = 0, q = 0;
+    cudaEventElapsedTime(&k, ctx->ev0, ctx->ev1); cudaEventElapsedTime(&q, ctx->ev1, ctx->ev2);
+    ctx->stats.kernel_ms = k; ctx->stats.post_ms = q;
+    ctx->stats.samples = (uint64_t)px * (uint64_t)spp;
+    ctx->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    if (cb) cb(1.0, user);                                          // ray-tracer.js:279
+    return BRT_OK;
+}
+
+void brt_cancel(brt_ctx* ctx) { if (ctx) ctx->cancel.store(1); }
+
+int brt_get_stats(brt_ctx* ctx, brt_stats* out) {
+    if (!ctx || !out) return BRT_E_INVALID;
+    if (ctx->device >= 0 && ctx->rp.count_tests && ctx->dCounters.p) {
+        CK(cudaSetDevice(ctx->device));
+        unsigned long long c[8];
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpy(c, ctx->dCounters.p, sizeof(c), cudaMemcpyDeviceToHost));
+        ctx->stats.rays = c[0]; ctx->stats.tests_sphere = c[1]; ctx->stats.tests_plane = c[2]; ctx->stats.tests_box = c[3];
+        ctx->stats.tests_tri_a = c[4]; ctx->stats.tests_tri_b = c[5]; ctx->stats.tests_tri_c = c[6]; ctx->stats.tests_aabb = c[7];
+    }
+    *out = ctx->stats;
+    return BRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------- parity AOVs
+int brt_primary_aov_f32(brt_ctx* ctx, int32_t* obj_id, int32_t* tri_id, float* t, float* normal3, uint8_t* front_face) {
+    if (!ctx || !obj_id || !tri_id || !t || !normal3 || !front_face) return BRT_E_INVALID;
+    PTParams p;
+    int rc = prepare(ctx, p);
+    if (rc != BRT_OK) return rc;
+    size_t px = (size_t)p.W * p.H;
+    CK(ctx->dScratch.ensure(px * (4 + 4 + 4 + 12 + 1) + 64));
+    char* base = (char*)ctx->dScratch.p;
+    int* dObj = (int*)base; int* dTri = (int*)(base + px * 4); float* dT = (float*)(base + px * 8); float* dN = (float*)(base + px * 12);
+    unsigned char* dF = (unsigned char*)(base + px * 24);
+    CK(launch_primary_aov(p, use_bvh(ctx), dObj, dTri, dT, dN, dF, ctx->stream));
+    CK(cudaMemcpyAsync(obj_id, dObj, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(tri_id, dTri, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(t, dT, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(normal3, dN, px * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(front_face, dF, px, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRT_OK;
+}
+
+int brt_primary_aov_f64(brt_ctx* ctx, int32_t* obj_id, int32_t* tri_id, double* t, double* normal3, uint8_t* front_face) {
+    if (!ctx || !obj_id || !tri_id || !t || !normal3 || !front_face) return BRT_E_INVALID;
+    NEED_GPU();
+    if (!ctx->haveScene) return fail(ctx, BRT_E_NOSCENE, "no scene loaded");
+    if (!ctx->haveCam) return fail(ctx, BRT_E_NOSCENE, "no camera set");
+    CK(cudaSetDevice(ctx->device));
+    const HostScene& s = ctx->scene;
+    if (ctx->obj64Dirty) {
+        std::vector<Obj64> objs(s.objects.size());
+        for (size_t i = 0; i < s.objects.size(); i++) {
+            const brt_object& o = s.objects[i]; Obj64& d = objs[i];
+            d.type = o.type; d.material = o.material; d.firstTri = o.first_tri; d.triCount = o.tri_count;
+            for (int k = 0; k < 3; k++) { d.a[k] = o.a[k]; d.b[k] = o.b[k]; d.c[k] = o.c[k]; }
+        }
+        CK(ctx->dObj64.ensure(objs.size() * sizeof(Obj64)));
+        if (!objs.empty()) CK(cudaMemcpy(ctx->dObj64.p, objs.data(), objs.size() * sizeof(Obj64), cudaMemcpyHostToDevice));
+        CK(ctx->dTris64.ensure(s.meshTris.size() * sizeof(double)));
+        if (!s.meshTris.empty()) CK(cudaMemcpy(ctx->dTris64.p, s.meshTris.data(), s.meshTris.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ctx->obj64Dirty = false;
+    }
+    Cam64 c{};
+    for (int k = 0; k < 3; k++) {
+        c.origin[k] = ctx->cam.origin[k]; c.llc[k] = ctx->cam.lower_left_corner[k]; c.horizontal[k] = ctx->cam.horizontal[k];
+        c.vertical[k] = ctx->cam.vertical[k]; c.w[k] = ctx->cam.w[k];
+    }
+    c.type = ctx->cam.type;
+    const int W = ctx->rp.width, H = ctx->rp.height;
+    size_t px = (size_t)W * H;
+    CK(ctx->dScratch.ensure(px * (4 + 4 + 8 + 24 + 1) + 64));
+    char* base = (char*)ctx->dScratch.p;
+    double* dT = (double*)base; double* dN = (double*)(base + px * 8); int* dObj = (int*)(base + px * 32); int* dTri = (int*)(base + px * 36);
+    unsigned char* dF = (unsigned char*)(base + px * 40);
+    CK(launch_primary_aov64((const Obj64*)ctx->dObj64.p, (int)s.objects.size(), (const double*)ctx->dTris64.p, c, W, H, dObj, dTri, dT, dN, dF, ctx->stream));
+    CK(cudaMemcpyAsync(obj_id, dObj, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(tri_id, dTri, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(t, dT, px * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(normal3, dN, px * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(front_face, dF, px, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------- unit hooks
+int brt_eval_background(brt_ctx* ctx, const double* dirs, int n, float* out_rgb) {
+    if (!ctx || !dirs || !out_rgb || n < 0) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_perm(ctx);
+    if (rc != BRT_OK) return rc;
+    if (n == 0) return BRT_OK;
+    std::vector<float> f(3 * (size_t)n);
+    for (size_t i = 0; i < f.size(); i++) f[i] = (float)dirs[i];
+    CK(ctx->dScratch.ensure(f.size() * 8));
+    float* dIn = (float*)ctx->dScratch.p; float* dOut = dIn + f.size();
+    CK(cudaMemcpyAsync(dIn, f.data(), f.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    DevScene sc = ctx->dev;
+    sc.bgKind = ctx->bg.kind; sc.bgR = (float)ctx->bg.color[0]; sc.bgG = (float)ctx->bg.color[1]; sc.bgB = (float)ctx->bg.color[2];
+    sc.skyIntensity = (float)ctx->bg.intensity;
+    CK(launch_eval_background(sc, dIn, n, dOut, ctx->stream));
+    CK(cudaMemcpyAsync(out_rgb, dOut, f.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRT_OK;
+}
+
+int brt_debug_rng_stream(brt_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, int n, float* out) {
+    if (!ctx || !out || n < 0) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return BRT_OK;
+    CK(ctx->dScratch.ensure((size_t)n * 4));
+    CK(launch_rng_stream((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, n, (float*)ctx->dScratch.p, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->dScratch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRT_OK;
+}
+
+int brt_postprocess_host(brt_ctx* ctx, const float* linear_mean, uint8_t* rgba8, float* float_data) {
+    if (!ctx || !linear_mean || !rgba8) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    const size_t px = (size_t)ctx->rp.width * ctx->rp.height;
+    // a linear-mean image is an accumulation buffer with one sample per pixel
+    std::vector<float> acc(linear_mean, linear_mean + px * 4);
+    for (size_t i = 0; i < px; i++) acc[4 * i + 3] = 1.0f;
+    CK(ctx->dAccum.ensure(px * 16)); CK(ctx->dRgba.ensure(px * 4)); CK(ctx->dFloat.ensure(px * 16));
+    CK(cudaMemcpyAsync(ctx->dAccum.p, acc.data(), px * 16, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = brt_resolve_device(ctx, (const float*)ctx->dAccum.p, (uint8_t*)ctx->dRgba.p, (float*)ctx->dFloat.p, nullptr);
+    if (rc != BRT_OK) return rc;
+    CK(cudaMemcpyAsync(rgba8, ctx->dRgba.p, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (float_data) CK(cudaMemcpyAsync(float_data, ctx->dFloat.p, px * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRT_OK;
+}
+
+int brt_measure_fp32_peak(brt_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    CK(ctx->dScratch.ensure(64));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    CK(launch_fp32_peak((float*)ctx->dScratch.p, blocks, 64, ctx->stream));           // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(launch_fp32_peak((float*)ctx->dScratch.p, blocks, iters, ctx->stream));
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        double flops = (double)blocks * 256 * (double)iters * 16 * 8 * 2;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    *tflops = best;
+    return BRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// Device-side core of libbrt: scene views, Philox RNG, fp32 intersection, BVH traversal, materials and
+// backgrounds.  Every routine cites the reference JavaScript it reproduces (Shinzef/BlenderRayTracer).
+// This is new sm_100a code, not a translation: SoA float4 primitive arrays read with 128-bit loads through
+// the read-only path, an Aila–Laine style 64-byte two-child BVH node, a shared-memory traversal stack, and
+// counter-based RNG so that every (pixel, sample) is independent of how work is partitioned.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+
+namespace brt {
+
+// ------------------------------------------------------------------------------------------- ids
+// A primitive id packs the primitive type (bits 28..29) and its index within the type's array.
+// Bit 31 marks a BVH leaf reference on the traversal stack.
+constexpr uint32_t PID_NONE = 0x7FFFFFFFu;
+constexpr uint32_t LEAF_BIT = 0x80000000u;
+enum PrimType : uint32_t { PT_SPHERE = 0, PT_PLANE = 1, PT_BOX = 2, PT_TRI = 3 };
+__host__ __device__ inline uint32_t make_pid(uint32_t type, uint32_t idx) { return (type << 28) | idx; }
+__host__ __device__ inline uint32_t pid_type(uint32_t pid) { return (pid >> 28) & 3u; }
+__host__ __device__ inline uint32_t pid_index(uint32_t pid) { return pid & 0x0FFFFFFFu; }
+
+// ------------------------------------------------------------------------------------------- scene views
+struct DevScene {
+    const float4* sph;   // (cx, cy, cz, r)                                  geometry.js:9-13
+    const float4* pln;   // 2 per plane: (n.xyz, 0), (p.xyz, 0)              geometry.js:50-54
+    const float4* box;   // 2 per box: min, max                              geometry.js:79-83
+    const float4* tri;   // 3 per triangle: v0, e1 = v1-v0, e2 = v2-v0       geometry.js:137-146
+    const int4* meta;    // per primitive (unified index): {objId, matId, triId, 0}
+    const float4* mat;   // (r, g, b, param)                                 materials.js
+    const int* matType;  // BRT_MAT_*
+    const float4* nodes; // 4 x float4 per BVH node (see bvh.cu)
+    const float4* lights;// 2 per light: (v.xyz, type), (color*intensity .xyz, 0)
+    const unsigned char* perm;  // 512-entry doubled Perlin permutation      noise.js:7-17
+    int nSph, nPln, nBox, nTri;
+    int baseSph, basePln, baseBox, baseTri;   // offsets into meta
+    int nNodes, nLights;
+    int bgKind;
+    float bgR, bgG, bgB, skyIntensity;
+    int bvhStackDepth;
+};
+
+struct DevCamera {         // camera.js:14-35 (derived on the host in float64, rounded once to fp32)
+    float ox, oy, oz;
+    float llx, lly, llz;
+    float hx, hy, hz;
+    float vx, vy, vz;
+    float ux, uy, uz;      // camera.u
+    float wx, wy, wz;      // camera.w
+    float vvx, vvy, vvz;   // camera.v
+    float lensRadius;
+    int type;
+};
+
+struct Counters {          // counting build
+    unsigned long long rays, sph, pln, box, triA, triB, triC, aabb;
+};
+
+// ------------------------------------------------------------------------------------------- float3 helpers
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize0(float3 a) {                  // math.js:18 (zero vector stays zero)
+    float l2 = dot(a, a);
+    return l2 > 0.f ? a * rsqrtf(l2) : f3(0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 reflect(float3 v, float3 n) { return v - n * (2.f * dot(v, n)); }   // math.js:19
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------- Philox4x32-10
+// Stands in for Math.random (math.js:21-31).  counter = (pixel, sample, block, tag), key = seed.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+constexpr uint32_t PHILOX_TAG = 0x42525431u;   // "BRT1"
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// Sequential stream for BRT_SAMPLER_REFERENCE: the reference's draw order, one uniform at a time.
+struct RngSeq {
+    uint32_t pix, samp, blk, k0, k1;
+    uint4 buf;
+    int have;
+    __device__ __forceinline__ void init(uint32_t pixel, uint32_t sample, uint32_t seedLo, uint32_t seedHi) {
+        pix = pixel; samp = sample; blk = 0; k0 = seedLo; k1 = seedHi; have = 0;
+    }
+    __device__ __forceinline__ float next() {
+        if (have == 0) { buf = philox4x32_10(pix, samp, blk, PHILOX_TAG, k0, k1); blk++; have = 4; }
+        uint32_t v = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
+        have--;
+        return u01(v);
+    }
+};
+
+// ------------------------------------------------------------------------------------------- primitive tests
+// All tests return the candidate parametric t chosen by the reference's root-selection logic for t >= tMin
+// (tMin = 0.001, ray-tracer.js:105); the caller applies the `t > closestT` rejection and the tie rule.
+// `self` = the ray starts ON this primitive.  In exact arithmetic one root is then exactly 0 (< tMin, always
+// rejected by the reference); in fp32 it is noise of either sign, so that root is dropped analytically.
+
+// geometry.js:15-29.  Discriminant evaluated as a*(r^2 - |oc - (hb/a) D|^2) (cancellation-robust form of hb^2 - a c).
+__device__ __forceinline__ bool hit_sphere(float4 s, float3 O, float3 D, float a, float inva, float tMin, bool self, float& t) {
+    float3 oc = f3(O.x - s.x, O.y - s.y, O.z - s.z);
+    float hb = dot(oc, D);
+    if (self) { t = -2.f * hb * inva; return t >= tMin; }
+    float k = hb * inva;
+    float3 l = f3(oc.x - k * D.x, oc.y - k * D.y, oc.z - k * D.z);
+    float disc = s.w * s.w - dot(l, l);
+    if (disc < 0.f) return false;
+    float sq = sqrtf(a * disc);
+    float root = (-hb - sq) * inva;
+    if (root < tMin) {
+        root = (-hb + sq) * inva;
+        if (!(root >= tMin)) return false;
+    }
+    t = root;
+    return true;
+}
+// geometry.js:56-61
+__device__ __forceinline__ bool hit_plane(float4 n, float4 p, float3 O, float3 D, float tMin, float& t) {
+    float denom = n.x * D.x + n.y * D.y + n.z * D.z;
+    if (fabsf(denom) < 1e-6f) return false;
+    float tt = ((p.x - O.x) * n.x + (p.y - O.y) * n.y + (p.z - O.z) * n.z) / denom;
+    if (!(tt >= tMin)) return false;
+    t = tt;
+    return true;
+}
+// geometry.js:85-112.  `face` returns 0..5 = x-,x+,y-,y+,z-,z+ : the slab plane that produced t (the reference picks
+// the face by |p - face| < 1e-6, :119-126, which is the same face away from edges; ties resolve x, y, z as there).
+__device__ __forceinline__ bool hit_box(float4 mn, float4 mx, float3 O, float3 D, float3 inv, float tMin, bool self, float& t, int& face) {
+    float t0 = (mn.x - O.x) * inv.x, t1 = (mx.x - O.x) * inv.x;
+    int fe = 0, fx = 1;                         // entering / exiting face ids
+    if (t0 > t1) { float tmp = t0; t0 = t1; t1 = tmp; fe = 1; fx = 0; }
+    float y0 = (mn.y - O.y) * inv.y, y1 = (mx.y - O.y) * inv.y;
+    int fye = 2, fyx = 3;
+    if (y0 > y1) { float tmp = y0; y0 = y1; y1 = tmp; fye = 3; fyx = 2; }
+    if (t0 > y1 || y0 > t1) return false;
+    if (y0 > t0) { t0 = y0; fe = fye; }         // Math.max(tMinBox, tMinY): x wins ties
+    if (y1 < t1) { t1 = y1; fx = fyx; }
+    float z0 = (mn.z - O.z) * inv.z, z1 = (mx.z - O.z) * inv.z;
+    int fze = 4, fzx = 5;
+    if (z0 > z1) { float tmp = z0; z0 = z1; z1 = tmp; fze = 5; fzx = 4; }
+    if (t0 > z1 || z0 > t1) return false;
+    if (z0 > t0) { t0 = z0; fe = fze; }
+    if (z1 < t1) { t1 = z1; fx = fzx; }
+    float tt; int ff;
+    if (self) {
+        // origin on the box surface: drop the root nearest to zero, keep the other (see header comment)
+        if (fabsf(t0) < fabsf(t1)) { tt = t1; ff = fx; } else { tt = t0; ff = fe; }
+        if (!(tt >= tMin)) return false;
+    } else {
+        if (t0 > tMin) { tt = t0; ff = fe; } else { tt = t1; ff = fx; }
+        if (!(tt >= tMin)) return false;
+    }
+    t = tt; face = ff;
+    return true;
+}
+// geometry.js:148-175 (Möller–Trumbore with the reference's absolute 1e-4 parallel threshold).
+template <bool COUNT>
+__device__ __forceinline__ bool hit_tri(float4 v0, float4 e1, float4 e2, float3 O, float3 D, float tMin, float& t, Counters& cnt) {
+    float3 E1 = xyz(e1), E2 = xyz(e2);
+    float3 h = cross(D, E2);
+    float a = dot(E1, h);
+    if (fabsf(a) < 0.0001f) return false;
+    float f = 1.0f / a;
+    float3 s = f3(O.x - v0.x, O.y - v0.y, O.z - v0.z);
+    float u = f * dot(s, h);
+    if (u < 0.f || u > 1.f) return false;
+    if (COUNT) cnt.triB++;
+    float3 q = cross(s, E1);
+    float v = f * dot(D, q);
+    if (v < 0.f || u + v > 1.f) return false;
+    if (COUNT) cnt.triC++;
+    float tt = f * dot(E2, q);
+    if (!(tt >= tMin)) return false;
+    t = tt;
+    return true;
+}
+
+struct Hit {
+    float t;
+    uint32_t pid;
+    int face;      // box face id when pid is a box
+};
+
+// Tie rule: across objects the FIRST object wins an exact tie (world.js:26 `hit.t < closestT`);
+// inside one mesh the LAST triangle wins (geometry.js:175 accepts t == tMax, :255-258 replaces).
+__device__ __forceinline__ int meta_index(const DevScene& sc, uint32_t pid) {
+    uint32_t ty = pid_type(pid), ix = pid_index(pid);
+    int base = ty == PT_SPHERE ? sc.baseSph : ty == PT_PLANE ? sc.basePln : ty == PT_BOX ? sc.baseBox : sc.baseTri;
+    return base + (int)ix;
+}
+static __device__ __noinline__ bool tie_wins(const DevScene& sc, uint32_t cand, uint32_t cur) {
+    int4 mc = __ldg(&sc.meta[meta_index(sc, cand)]);
+    int4 mb = __ldg(&sc.meta[meta_index(sc, cur)]);
+    if (mc.x != mb.x) return mc.x < mb.x;
+    return mc.z > mb.z;
+}
+template <bool SHADOW>
+__device__ __forceinline__ void consider(const DevScene& sc, Hit& best, float t, uint32_t pid, int face) {
+    if (SHADOW) {
+        // any-hit for the direct-lighting extension: strictly closer than the light, emissive primitives ignored
+        if (t < best.t) {
+            int4 m = __ldg(&sc.meta[meta_index(sc, pid)]);
+            if (__ldg(&sc.matType[m.y]) != 3) { best.t = t; best.pid = pid; best.face = face; }
+        }
+        return;
+    }
+    if (t < best.t || (t == best.t && best.pid != PID_NONE && tie_wins(sc, pid, best.pid))) {
+        best.t = t; best.pid = pid; best.face = face;
+    }
+}
+
+template <bool COUNT, bool SHADOW>
+__device__ __forceinline__ void test_prim(const DevScene& sc, uint32_t pid, float3 O, float3 D, float3 inv, float a, float inva,
+                                          float tMin, uint32_t self, Hit& best, Counters& cnt) {
+    uint32_t ty = pid_type(pid), ix = pid_index(pid);
+    float t; int face = 0;
+    bool h;
+    if (ty == PT_TRI) {
+        if (pid == self) return;                  // a ray leaving a planar primitive cannot meet it again
+        if (COUNT) cnt.triA++;
+        h = hit_tri<COUNT>(ldg4(sc.tri + 3 * ix), ldg4(sc.tri + 3 * ix + 1), ldg4(sc.tri + 3 * ix + 2), O, D, tMin, t, cnt);
+    } else if (ty == PT_SPHERE) {
+        if (COUNT) cnt.sph++;
+        h = hit_sphere(ldg4(sc.sph + ix), O, D, a, inva, tMin, pid == self, t);
+    } else {
+        if (COUNT) cnt.box++;
+        h = hit_box(ldg4(sc.box + 2 * ix), ldg4(sc.box + 2 * ix + 1), O, D, inv, tMin, pid == self, t, face);
+    }
+    if (h && t <= best.t) consider<SHADOW>(sc, best, t, pid, face);
+}
+
+// Unbounded planes live outside the BVH in a linear list (world.js:24-30 order is irrelevant given the tie rule).
+template <bool COUNT, bool SHADOW>
+__device__ __forceinline__ void test_planes(const DevScene& sc, float3 O, float3 D, float tMin, uint32_t self, Hit& best, Counters& cnt) {
+    for (int i = 0; i < sc.nPln; i++) {
+        uint32_t pid = make_pid(PT_PLANE, i);
+        if (pid == self) continue;
+        if (COUNT) cnt.pln++;
+        float t;
+        if (hit_plane(ldg4(sc.pln + 2 * i), ldg4(sc.pln + 2 * i + 1), O, D, tMin, t) && t <= best.t) consider<SHADOW>(sc, best, t, pid, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- closest hit
+// Brute force: the reference's own O(N) loops (world.js:24-30, geometry.js:253-259) over the SoA arrays.
+template <bool COUNT, bool SHADOW>
+__device__ __forceinline__ Hit trace_brute(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt) {
+    Hit best; best.t = tMax; best.pid = PID_NONE; best.face = 0;
+    float a = dot(D, D), inva = 1.0f / a;
+    float3 inv = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
+    test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
+    for (int i = 0; i < sc.nSph; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_SPHERE, i), O, D, inv, a, inva, tMin, self, best, cnt);
+    for (int i = 0; i < sc.nBox; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_BOX, i), O, D, inv, a, inva, tMin, self, best, cnt);
+    for (int i = 0; i < sc.nTri; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_TRI, i), O, D, inv, a, inva, tMin, self, best, cnt);
+    return best;
+}
+
+// BVH node (64 B, four 128-bit loads):
+//   n0 = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)   n1 = same for child 1
+//   n2 = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)   n3 = (child0, child1, -, -) as bit patterns;
+//   a child with LEAF_BIT set is a primitive id, otherwise an internal node index.
+// Traversal stack: the first SMEM_STACK entries of every thread live in shared memory ([depth][thread], conflict
+// free); deeper entries (rare) spill to a per-thread local array.
+constexpr int SMEM_STACK = 20;
+constexpr int LOCAL_STACK = 44;
+
+template <bool COUNT, bool SHADOW>
+__device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
+                                         uint32_t* sstack /* &smem[threadIdx.x] */, int sstride) {
+    Hit best; best.t = tMax; best.pid = PID_NONE; best.face = 0;
+    float a = dot(D, D), inva = 1.0f / a;
+    float3 inv = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
+    test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
+    if (sc.nNodes == 0) return best;
+    float3 ood = f3(O.x * inv.x, O.y * inv.y, O.z * inv.z);
+    uint32_t lstack[LOCAL_STACK];
+    int sp = 0;
+    uint32_t cur = 0;
+    const float4* __restrict__ nodes = sc.nodes;
+    for (;;) {
+        if (cur & LEAF_BIT) {
+            test_prim<COUNT, SHADOW>(sc, cur & ~LEAF_BIT, O, D, inv, a, inva, tMin, self, best, cnt);
+            if (SHADOW && best.pid != PID_NONE) break;
+        } else {
+            const float4* np = nodes + 4 * (size_t)cur;
+            float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
+            float4 n3f = ldg4(np + 3);
+            uint32_t c0 = __float_as_uint(n3f.x), c1 = __float_as_uint(n3f.y);
+            if (COUNT) cnt.aabb += 2;
+            float ax0 = fmaf(n0.x, inv.x, -ood.x), ax1 = fmaf(n0.y, inv.x, -ood.x);
+            float ay0 = fmaf(n0.z, inv.y, -ood.y), ay1 = fmaf(n0.w, inv.y, -ood.y);
+            float az0 = fmaf(n2.x, inv.z, -ood.z), az1 = fmaf(n2.y, inv.z, -ood.z);
+            float bx0 = fmaf(n1.x, inv.x, -ood.x), bx1 = fmaf(n1.y, inv.x, -ood.x);
+            float by0 = fmaf(n1.z, inv.y, -ood.y), by1 = fmaf(n1.w, inv.y, -ood.y);
+            float bz0 = fmaf(n2.z, inv.z, -ood.z), bz1 = fmaf(n2.w, inv.z, -ood.z);
+            float tn0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.f));
+            float tf0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best.t));
+            float tn1 = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.f));
+            float tf1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), best.t));
+            // conservative: boxes are inflated at build time and the far bound is widened by a few ulps, so the BVH can
+            // only add candidates, never lose one the brute-force loop would have found.
+            bool h0 = tn0 <= tf0 * 1.0000005f, h1 = tn1 <= tf1 * 1.0000005f;
+            if (h0 | h1) {
+                if (h0 & h1) {
+                    bool swap = tn1 < tn0;
+                    uint32_t nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+                    if (sp < SMEM_STACK) sstack[sp * sstride] = farc; else lstack[sp - SMEM_STACK] = farc;
+                    sp++;
+                    cur = nearc;
+                } else cur = h0 ? c0 : c1;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        sp--;
+        cur = sp < SMEM_STACK ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------- surface frame
+struct Surface {
+    float3 P, N;        // hit point, shading normal after setFaceNormal (math.js:55-58)
+    bool front;
+    int objId, matId, triId;
+};
+__device__ __forceinline__ Surface make_surface(const DevScene& sc, const Hit& h, float3 O, float3 D) {
+    Surface s;
+    s.P = f3(O.x + h.t * D.x, O.y + h.t * D.y, O.z + h.t * D.z);          // Ray.at (math.js:41)
+    uint32_t ty = pid_type(h.pid), ix = pid_index(h.pid);
+    int4 m = __ldg(&sc.meta[meta_index(sc, h.pid)]);
+    s.objId = m.x; s.matId = m.y; s.triId = m.z;
+    float3 n;
+    if (ty == PT_SPHERE) {
+        float4 sp = ldg4(sc.sph + ix);
+        float ir = 1.0f / sp.w;                                            // geometry.js:34 (negative radius flips)
+        n = f3((s.P.x - sp.x) * ir, (s.P.y - sp.y) * ir, (s.P.z - sp.z) * ir);
+    } else if (ty == PT_PLANE) {
+        n = xyz(ldg4(sc.pln + 2 * ix));
+    } else if (ty == PT_BOX) {
+        int f = h.face;
+        float sgn = (f & 1) ? 1.f : -1.f;
+        n = f3((f >> 1) == 0 ? sgn : 0.f, (f >> 1) == 1 ? sgn : 0.f, (f >> 1) == 2 ? sgn : 0.f);
+    } else {
+        n = normalize0(cross(xyz(ldg4(sc.tri + 3 * ix + 1)), xyz(ldg4(sc.tri + 3 * ix + 2))));   // geometry.js:143-145
+    }
+    s.front = dot(D, n) < 0.f;
+    s.N = s.front ? n : -n;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------- backgrounds (world.js:35-110)
+__device__ __forceinline__ float perlin_fade(float t) { return t * t * t * (t * (t * 6.f - 15.f) + 10.f); }      // noise.js:20
+__device__ __forceinline__ float perlin_grad(int hash, float x, float y, float z) {                               // noise.js:22-27
+    int h = hash & 15;
+    float u = h < 8 ? x : y;
+    float v = h < 4 ? y : (h == 12 || h == 14) ? x : z;
+    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+}
+__device__ __forceinline__ float lerpf(float t, float a, float b) { return a + t * (b - a); }                       // noise.js:21
+__device__ inline float perlin_noise(const unsigned char* __restrict__ p, float x, float y, float z) {             // noise.js:29-61
+    float flx = floorf(x), fly = floorf(y), flz = floorf(z);
+    int X = ((int)flx) & 255, Y = ((int)fly) & 255, Z = ((int)flz) & 255;
+    float fx = x - flx, fy = y - fly, fz = z - flz;
+    float u = perlin_fade(fx), v = perlin_fade(fy), w = perlin_fade(fz);
+    int A = p[X] + Y, AA = p[A] + Z, AB = p[A + 1] + Z;
+    int B = p[X + 1] + Y, BA = p[B] + Z, BB = p[B + 1] + Z;
+    return lerpf(w,
+        lerpf(v, lerpf(u, perlin_grad(p[AA], fx, fy, fz), perlin_grad(p[BA], fx - 1, fy, fz)),
+                 lerpf(u, perlin_grad(p[AB], fx, fy - 1, fz), perlin_grad(p[BB], fx - 1, fy - 1, fz))),
+        lerpf(v, lerpf(u, perlin_grad(p[AA + 1], fx, fy, fz - 1), perlin_grad(p[BA + 1], fx - 1, fy, fz - 1)),
+                 lerpf(u, perlin_grad(p[AB + 1], fx, fy - 1, fz - 1), perlin_grad(p[BB + 1], fx - 1, fy - 1, fz - 1))));
+}
+__device__ inline float3 background(const DevScene& sc, float3 D) {
+    float3 dir = normalize0(D);
+    float I = sc.skyIntensity;
+    switch (sc.bgKind) {
+    case 1:                                                                                                         // world.js:42-44
+        return f3(sc.bgR * I, sc.bgG * I, sc.bgB * I);
+    case 2: {                                                                                                       // world.js:74-110
+        const float il = 1.1952286093343936f;        // 1/|(-0.3,0.6,-0.5)|
+        float sunDot = fmaxf(0.f, (dir.x * -0.3f + dir.y * 0.6f + dir.z * -0.5f) * il);
+        float sunMask = sunDot > 0.96f ? 20.f : 0.f;
+        float corona = fmaxf(0.f, (sunDot - 0.8f) / 0.2f);
+        float c3 = corona * corona * 3.f;
+        float y = dir.y;
+        float sky = fmaxf(0.f, y * 0.5f + 0.5f) * 2.f;
+        float ground = fmaxf(0.f, -y * 0.3f);
+        float sc1 = fmaxf(0.f, 1.f - fabsf(y));
+        float scat = sc1 * sc1 * 0.3f;
+        return f3((0.3f * sky + 0.2f * ground + 0.8f * scat + 1.0f * sunMask + 1.0f * c3) * I,
+                  (0.5f * sky + 0.15f * ground + 0.9f * scat + 0.95f * sunMask + 0.8f * c3) * I,
+                  (0.8f * sky + 0.1f * ground + 1.0f * scat + 0.8f * sunMask + 0.6f * c3) * I);
+    }
+    case 3: {                                                                                                       // world.js:46-72
+        const float il = 0.95782628522115137f;       // 1/|(0.3,0.6,0.8)|
+        float sunDot = fmaxf(0.f, (dir.x * 0.3f + dir.y * 0.6f + dir.z * 0.8f) * il);
+        float s = sunDot;                             // pow(x, 512) by nine exact squarings
+#pragma unroll
+        for (int k = 0; k < 9; k++) s = s * s;
+        float sun = s * 10.f;
+        float hb = fmaxf(0.f, dir.y) * 0.8f;
+        float glow = expf(-fabsf(dir.y) * 4.f) * 0.3f;
+        float ground = fmaxf(0.f, -dir.y * 0.5f);
+        float cloud = fmaxf(0.f, perlin_noise(sc.perm, dir.x * 10.f, dir.y * 3.f + 2.f, dir.z * 10.f) * 0.8f + 0.2f);
+        float cl = cloud * fmaxf(0.f, dir.y) * 0.5f;
+        return f3((0.4f * hb + 1.0f * glow + 0.1f * ground + 1.0f * sun + 0.9f * cl) * I,
+                  (0.7f * hb + 0.8f * glow + 0.15f * ground + 0.95f * sun + 0.9f * cl) * I,
+                  (1.0f * hb + 0.6f * glow + 0.1f * ground + 0.8f * sun + 1.0f * cl) * I);
+    }
+    default: {                                                                                                      // world.js:35-40
+        float t = 0.5f * (dir.y + 1.0f);
+        return f3(((1.0f - t) + 0.5f * t) * I, ((1.0f - t) + 0.7f * t) * I, ((1.0f - t) + 1.0f * t) * I);
+    }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- sampling
+// math.js:22-31 by direct inversion (identical distributions; used by BRT_SAMPLER_FAST).
+__device__ __forceinline__ float3 uniform_sphere(float u0, float u1) {
+    float z = 1.f - 2.f * u0;
+    float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+    float sn, cs;
+    sincospif(2.f * u1, &sn, &cs);
+    return f3(r * cs, r * sn, z);
+}
+
+}  // namespace brt

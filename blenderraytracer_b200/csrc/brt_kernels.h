@@ -1,0 +1,70 @@
+// Host-visible declarations of the kernel launchers (one .cu per subsystem, linked into libbrt.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "brt_device.cuh"
+
+namespace brt {
+
+constexpr int PT_BLOCK = 128;
+
+struct PTParams {
+    DevScene sc;
+    DevCamera cam;
+    int W, H;
+    int sBegin, sCount;          // global sample indices [sBegin, sBegin + sCount) for every pixel
+    int maxDepth;
+    int aaMode;
+    uint32_t seedLo, seedHi;
+    int directLighting;
+    float4* accum;               // W*H fp32 RGBA sums (alpha = number of samples)
+    unsigned long long* counters;// 8 x u64 (Counters), counting build only
+};
+
+// pathtrace.cu
+cudaError_t launch_pathtrace(const PTParams& p, int sampler, bool useBvh, bool count, int zSplit, cudaStream_t st);
+cudaError_t launch_primary_aov(const PTParams& p, bool useBvh, int* objId, int* triId, float* t, float* nrm, unsigned char* front,
+                               cudaStream_t st);
+cudaError_t launch_eval_background(const DevScene& sc, const float* dirs, int n, float* out, cudaStream_t st);
+cudaError_t launch_rng_stream(uint32_t lo, uint32_t hi, uint32_t pixel, uint32_t sample, int n, float* out, cudaStream_t st);
+cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st);
+
+// post.cu  (ray-tracer.js:208-233, 266-276; post-processor.js)
+struct PostParams {
+    int W, H;
+    int tonemap;
+    double exposure, invGamma;
+    double w1, w2;               // exp(-1/(2σ²)), exp(-2/(2σ²)) computed on the host in float64 (post-processor.js:59)
+};
+// accum (sum, alpha = count) -> rgba8 [+ floatData] [+ linear mean]; rows [rowBegin,rowEnd)
+cudaError_t launch_resolve(const PostParams& pp, const float4* accum, uchar4* rgba, float4* floatData, float4* linear,
+                           int rowBegin, int rowEnd, cudaStream_t st);
+// sums rows of nPeers accumulation buffers in rank order, then resolves (fused NVLink reduce + resolve)
+cudaError_t launch_reduce_resolve(const PostParams& pp, const float4* const* peers, int nPeers, uchar4* rgba, float4* floatData,
+                                  int rowBegin, int rowEnd, cudaStream_t st);
+cudaError_t launch_denoise(const PostParams& pp, const float4* floatData, uchar4* rgba, float4* outFloat, cudaStream_t st);
+
+// aov64.cu — float64, FMA-free, brute-force primary visibility with the reference's exact operation order
+struct Obj64 {                   // one per world.objects entry, in order
+    int type, material;
+    double a[3], b[3], c[3];     // as brt_object (plane normal already normalised, geometry.js:52)
+    long long firstTri, triCount;
+};
+struct Cam64 {
+    double origin[3], llc[3], horizontal[3], vertical[3], w[3];
+    int type;
+};
+cudaError_t launch_primary_aov64(const Obj64* objs, int nObjs, const double* meshTris /* 9 per tri */, const Cam64& cam, int W, int H,
+                                 int* objId, int* triId, double* t, double* nrm, unsigned char* front, cudaStream_t st);
+
+// bvh.cu — GPU LBVH: Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit
+struct BvhBuildResult {
+    float4* nodes;               // device, 4 x float4 per node, root = 0 (cudaMalloc'd; caller frees)
+    long long nNodes;
+    int depth;
+    float buildMs;
+};
+// prim AABBs are computed on the device from the SoA arrays; pids = primitive ids of the bounded primitives
+cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st);
+
+}  // namespace brt

@@ -1,0 +1,295 @@
+// GPU LBVH build over the bounded primitives (spheres, boxes, triangles):
+//   k_prim_bounds → k_scene_bounds → k_morton → 4-pass LSD radix sort (k_sort_hist / k_sort_scan / k_sort_scatter)
+//   → k_karras (Karras 2012 hierarchy from sorted 30-bit Morton codes, index tie-break) → k_refit (bottom-up AABBs).
+// The reference has no acceleration structure (README.md:102 lists it as future work; world.js:24-30 and
+// geometry.js:253-259 are linear loops); the BVH must therefore be invisible in the results: boxes are padded
+// and traversal (brt_device.cuh) resolves exact ties by the reference's loop-order rule.
+// Node layout (64 B): n0 = child0 (min.x,max.x,min.y,max.y); n1 = child1 (same); n2 = (c0.min.z,c0.max.z,c1.min.z,c1.max.z);
+// n3 = (child0, child1, 0, 0) bit patterns, LEAF_BIT | pid for leaves.
+#include "brt_kernels.h"
+#include <cfloat>
+
+namespace brt {
+
+struct Aabb { float mn[3], mx[3]; };
+
+__device__ __forceinline__ Aabb prim_aabb(const DevScene& sc, uint32_t pid) {
+    uint32_t ty = pid_type(pid), ix = pid_index(pid);
+    Aabb b;
+    if (ty == PT_SPHERE) {
+        float4 s = sc.sph[ix]; float r = fabsf(s.w);
+        b.mn[0] = s.x - r; b.mn[1] = s.y - r; b.mn[2] = s.z - r; b.mx[0] = s.x + r; b.mx[1] = s.y + r; b.mx[2] = s.z + r;
+    } else if (ty == PT_BOX) {
+        float4 a = sc.box[2 * ix], c = sc.box[2 * ix + 1];
+        b.mn[0] = fminf(a.x, c.x); b.mn[1] = fminf(a.y, c.y); b.mn[2] = fminf(a.z, c.z);
+        b.mx[0] = fmaxf(a.x, c.x); b.mx[1] = fmaxf(a.y, c.y); b.mx[2] = fmaxf(a.z, c.z);
+    } else {
+        float4 v0 = sc.tri[3 * ix], e1 = sc.tri[3 * ix + 1], e2 = sc.tri[3 * ix + 2];
+        float p1[3] = { v0.x + e1.x, v0.y + e1.y, v0.z + e1.z }, p2[3] = { v0.x + e2.x, v0.y + e2.y, v0.z + e2.z };
+        float p0[3] = { v0.x, v0.y, v0.z };
+        for (int k = 0; k < 3; k++) { b.mn[k] = fminf(p0[k], fminf(p1[k], p2[k])); b.mx[k] = fmaxf(p0[k], fmaxf(p1[k], p2[k])); }
+    }
+    // conservative padding: fp32 slab / primitive-test rounding must never cull a primitive the brute-force loop would hit
+    float ext = fmaxf(b.mx[0] - b.mn[0], fmaxf(b.mx[1] - b.mn[1], b.mx[2] - b.mn[2]));
+    for (int k = 0; k < 3; k++) {
+        float pad = 1e-5f * fmaxf(fmaxf(fabsf(b.mn[k]), fabsf(b.mx[k])), ext) + 1e-7f;
+        b.mn[k] -= pad; b.mx[k] += pad;
+    }
+    return b;
+}
+__device__ __forceinline__ uint32_t bounded_pid(const DevScene& sc, int i) {
+    if (i < sc.nSph) return make_pid(PT_SPHERE, i);
+    i -= sc.nSph;
+    if (i < sc.nBox) return make_pid(PT_BOX, i);
+    return make_pid(PT_TRI, i - sc.nBox);
+}
+
+__global__ void k_prim_bounds(DevScene sc, int n, Aabb* boxes, float* blockBounds /* 6 per block */) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float c[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    if (i < n) {
+        Aabb b = prim_aabb(sc, bounded_pid(sc, i));
+        boxes[i] = b;
+        for (int k = 0; k < 3; k++) { float m = 0.5f * (b.mn[k] + b.mx[k]); c[k] = m; c[3 + k] = m; }
+    }
+    __shared__ float red[6][8];
+    for (int k = 0; k < 6; k++) {
+        float v = c[k];
+        for (int o = 16; o > 0; o >>= 1) { float w = __shfl_down_sync(0xffffffffu, v, o); v = k < 3 ? fminf(v, w) : fmaxf(v, w); }
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        int k = threadIdx.x; float v = red[k][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = k < 3 ? fminf(v, red[k][w]) : fmaxf(v, red[k][w]);
+        blockBounds[6 * blockIdx.x + k] = v;
+    }
+}
+__global__ void k_scene_bounds(const float* blockBounds, int nBlocks, float* out6) {
+    __shared__ float red[6][256];
+    for (int k = 0; k < 6; k++) {
+        float v = k < 3 ? FLT_MAX : -FLT_MAX;
+        for (int b = threadIdx.x; b < nBlocks; b += blockDim.x) { float w = blockBounds[6 * b + k]; v = k < 3 ? fminf(v, w) : fmaxf(v, w); }
+        red[k][threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        int k = threadIdx.x; float v = red[k][0];
+        for (int i = 1; i < (int)blockDim.x; i++) v = k < 3 ? fminf(v, red[k][i]) : fmaxf(v, red[k][i]);
+        out6[k] = v;
+    }
+}
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__global__ void k_morton(const Aabb* boxes, int n, const float* sb, uint32_t* keys, uint32_t* vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Aabb b = boxes[i];
+    uint32_t q[3];
+    for (int k = 0; k < 3; k++) {
+        float ext = sb[3 + k] - sb[k];
+        float x = ext > 0.f ? (0.5f * (b.mn[k] + b.mx[k]) - sb[k]) / ext : 0.f;
+        q[k] = (uint32_t)fminf(fmaxf(x * 1024.f, 0.f), 1023.f);
+    }
+    keys[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// ---- LSD radix sort, 8 bits per pass, stable ------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;                       // keys per thread per tile
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* keys, int n, int shift, uint32_t* hist, int nBlocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int base = blockIdx.x * SORT_TILE;
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        int i = base + k * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * nBlocks + blockIdx.x] = h[threadIdx.x];     // digit-major so one scan orders (digit, block)
+}
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* hist, int total) {
+    // single-block exclusive scan (total = 256 * nBlocks, tens of thousands of entries at most)
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += 1024) {
+        int i = base + threadIdx.x;
+        uint32_t v = i < total ? hist[i] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warpSums[threadIdx.x], s = w;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (threadIdx.x >= o) s += y; }
+            warpSums[threadIdx.x] = s - w;
+        }
+        __syncthreads();
+        uint32_t excl = x - v + warpSums[threadIdx.x >> 5] + carry;
+        if (i < total) hist[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* keysIn, const uint32_t* valsIn, uint32_t* keysOut,
+                                                               uint32_t* valsOut, int n, int shift, const uint32_t* hist, int nBlocks) {
+    __shared__ uint32_t offs[256];                   // running global offset of each digit for this block
+    __shared__ uint32_t wcount[SORT_THREADS / 32][256];
+    offs[threadIdx.x] = hist[threadIdx.x * nBlocks + blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = blockIdx.x * SORT_TILE;
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        for (int w = 0; w < SORT_THREADS / 32; w++) wcount[w][threadIdx.x] = 0;
+        __syncthreads();
+        int i = base + k * SORT_THREADS + threadIdx.x;
+        bool valid = i < n;
+        uint32_t key = valid ? keysIn[i] : 0xFFFFFFFFu, val = valid ? valsIn[i] : 0u;
+        uint32_t d = (key >> shift) & 255u;
+        uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFu);
+        uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rankInWarp == 0) wcount[warp][d] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            uint32_t before = 0;
+            for (int w = 0; w < warp; w++) before += wcount[w][d];
+            uint32_t dst = offs[d] + before + rankInWarp;
+            keysOut[dst] = key; valsOut[dst] = val;
+        }
+        __syncthreads();
+        uint32_t tot = 0;
+        for (int w = 0; w < SORT_THREADS / 32; w++) tot += wcount[w][threadIdx.x];
+        offs[threadIdx.x] += tot;
+        __syncthreads();
+    }
+}
+
+// ---- Karras hierarchy -------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+__global__ void k_karras(const uint32_t* keys, int n, int2* children /* n-1 */, int* parent /* 2n-1: internal [0,n-1), leaves [n-1,2n-1) */) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1) if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left = (lo == gamma) ? (n - 1 + gamma) : gamma;            // leaf ids are offset by n-1
+    int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
+    children[i] = make_int2(left, right);
+    parent[left] = i; parent[right] = i;
+    if (i == 0) parent[0] = -1;
+}
+__global__ void k_refit(const DevScene sc, int n, const uint32_t* sortedPrim, const Aabb* primBoxes, const int2* children, const int* parent,
+                        Aabb* nodeBox /* n-1 */, int* nodeDepth /* n-1 */, unsigned int* flags /* n-1, zeroed */, float4* nodes) {
+    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    int cur = parent[n - 1 + leaf];
+    while (cur >= 0) {
+        if (atomicAdd(&flags[cur], 1u) == 0u) return;               // first child to arrive stops; the second continues
+        __threadfence();
+        int2 ch = children[cur];
+        Aabb b[2]; int dep[2]; uint32_t ref[2];
+        int cc[2] = { ch.x, ch.y };
+        for (int k = 0; k < 2; k++) {
+            if (cc[k] >= n - 1) {
+                uint32_t pi = sortedPrim[cc[k] - (n - 1)];
+                b[k] = primBoxes[pi]; dep[k] = 0; ref[k] = LEAF_BIT | bounded_pid(sc, (int)pi);
+            } else {
+                // written by another thread before its atomicAdd + fence: read through L2
+                const volatile Aabb* vb = nodeBox + cc[k];
+                for (int a = 0; a < 3; a++) { b[k].mn[a] = vb->mn[a]; b[k].mx[a] = vb->mx[a]; }
+                dep[k] = ((const volatile int*)nodeDepth)[cc[k]]; ref[k] = (uint32_t)cc[k];
+            }
+        }
+        float4* np = nodes + 4 * (size_t)cur;
+        np[0] = make_float4(b[0].mn[0], b[0].mx[0], b[0].mn[1], b[0].mx[1]);
+        np[1] = make_float4(b[1].mn[0], b[1].mx[0], b[1].mn[1], b[1].mx[1]);
+        np[2] = make_float4(b[0].mn[2], b[0].mx[2], b[1].mn[2], b[1].mx[2]);
+        np[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), 0.f, 0.f);
+        Aabb u;
+        for (int a = 0; a < 3; a++) { u.mn[a] = fminf(b[0].mn[a], b[1].mn[a]); u.mx[a] = fmaxf(b[0].mx[a], b[1].mx[a]); }
+        nodeBox[cur] = u;
+        nodeDepth[cur] = 1 + max(dep[0], dep[1]);
+        __threadfence();
+        cur = parent[cur];
+    }
+}
+
+#define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return e_; } } while (0)
+
+cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st) {
+    out->nodes = nullptr; out->nNodes = 0; out->depth = 0; out->buildMs = 0.f;
+    const int n = sc.nSph + sc.nBox + sc.nTri;
+    if (n < 2) return cudaSuccess;                    // 0 or 1 bounded primitive: traversal falls back to the linear loop
+    Aabb *boxes = nullptr, *nodeBox = nullptr; float *blockBounds = nullptr, *sb = nullptr;
+    uint32_t *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr, *hist = nullptr; unsigned int* flags = nullptr;
+    int2* children = nullptr; int *parent = nullptr, *nodeDepth = nullptr; float4* nodes = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool ok = false;
+    auto cleanup = [&]() {
+        if (!ok) cudaFree(nodes);
+        cudaFree(boxes); cudaFree(nodeBox); cudaFree(blockBounds); cudaFree(sb); cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
+        cudaFree(hist); cudaFree(flags); cudaFree(children); cudaFree(parent); cudaFree(nodeDepth);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    const int nb = (n + 255) / 256, sortBlocks = (n + SORT_TILE - 1) / SORT_TILE;
+    BVH_CK(cudaMalloc(&boxes, sizeof(Aabb) * n)); BVH_CK(cudaMalloc(&nodeBox, sizeof(Aabb) * (n - 1)));
+    BVH_CK(cudaMalloc(&blockBounds, sizeof(float) * 6 * nb)); BVH_CK(cudaMalloc(&sb, sizeof(float) * 6));
+    BVH_CK(cudaMalloc(&k0, 4 * (size_t)n)); BVH_CK(cudaMalloc(&k1, 4 * (size_t)n)); BVH_CK(cudaMalloc(&v0, 4 * (size_t)n)); BVH_CK(cudaMalloc(&v1, 4 * (size_t)n));
+    BVH_CK(cudaMalloc(&hist, 4 * 256 * (size_t)sortBlocks)); BVH_CK(cudaMalloc(&flags, 4 * (size_t)(n - 1)));
+    BVH_CK(cudaMalloc(&children, sizeof(int2) * (n - 1))); BVH_CK(cudaMalloc(&parent, 4 * (size_t)(2 * n - 1)));
+    BVH_CK(cudaMalloc(&nodeDepth, 4 * (size_t)(n - 1)));
+    BVH_CK(cudaMalloc(&nodes, sizeof(float4) * 4 * (size_t)(n - 1)));
+    BVH_CK(cudaEventCreate(&e0)); BVH_CK(cudaEventCreate(&e1));
+    BVH_CK(cudaEventRecord(e0, st));
+    k_prim_bounds<<<nb, 256, 0, st>>>(sc, n, boxes, blockBounds);
+    k_scene_bounds<<<1, 256, 0, st>>>(blockBounds, nb, sb);
+    k_morton<<<nb, 256, 0, st>>>(boxes, n, sb, k0, v0);
+    uint32_t *ki = k0, *ko = k1, *vi = v0, *vo = v1;
+    for (int shift = 0; shift < 32; shift += 8) {
+        k_sort_hist<<<sortBlocks, SORT_THREADS, 0, st>>>(ki, n, shift, hist, sortBlocks);
+        k_sort_scan<<<1, 1024, 0, st>>>(hist, 256 * sortBlocks);
+        k_sort_scatter<<<sortBlocks, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, hist, sortBlocks);
+        uint32_t* t = ki; ki = ko; ko = t; t = vi; vi = vo; vo = t;
+    }
+    BVH_CK(cudaMemsetAsync(flags, 0, 4 * (size_t)(n - 1), st));
+    k_karras<<<(n - 1 + 255) / 256, 256, 0, st>>>(ki, n, children, parent);
+    k_refit<<<nb, 256, 0, st>>>(sc, n, vi, boxes, children, parent, nodeBox, nodeDepth, flags, nodes);
+    BVH_CK(cudaEventRecord(e1, st));
+    BVH_CK(cudaGetLastError());
+    BVH_CK(cudaEventSynchronize(e1));
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    int depth = 0;
+    BVH_CK(cudaMemcpy(&depth, nodeDepth, 4, cudaMemcpyDeviceToHost));
+    ok = true;
+    cleanup();
+    out->nodes = nodes; out->nNodes = n - 1; out->depth = depth; out->buildMs = ms;
+    return cudaSuccess;
+}
+
+}  // namespace brt
