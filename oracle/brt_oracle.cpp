@@ -842,6 +842,14 @@ void orc_quantize_image(const float* in, int w, int h, uint8_t* rgba) {         
         rgba[i] = quantize(in[i]); rgba[i + 1] = quantize(in[i + 1]); rgba[i + 2] = quantize(in[i + 2]); rgba[i + 3] = 255;
     }
 }
+// raw Philox4x32-10 block (Random123 known-answer vectors pin the generator itself)
+void orc_philox_raw(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+    Philox g(0, 0, 0);
+    g.key[0] = key2[0]; g.key[1] = key2[1];
+    for (int i = 0; i < 4; i++) g.ctr[i] = ctr4[i];
+    g.refill();
+    for (int i = 0; i < 4; i++) out4[i] = g.buf[i];
+}
 // first n uniforms of the (seed, pixel, sample) stream — lets tests pin the GPU's Philox against this one
 void orc_rng_stream(uint64_t seed, uint32_t pixel, uint32_t sample, int n, double* out) {
     Philox g(seed, pixel, sample);

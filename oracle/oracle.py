@@ -93,6 +93,7 @@ def lib():
     L.orc_refract.argtypes = [dp, dp, C.c_double, dp]
     L.orc_denoise.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_float)]
     L.orc_quantize_image.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    L.orc_philox_raw.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_rng_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, dp]
     L.orc_render_rect.argtypes = [C.c_void_p, C.POINTER(_RenderParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_uint8), C.POINTER(C.c_float), dp]
@@ -158,6 +159,9 @@ class OracleScene:
         self.cam_type_str = "perspective"
         self.bg_kind = "gradient"
         self.sky_intensity = 1.0
+        self.solid_color = (0.1, 0.1, 0.1)
+        self.objects_log = []     # (type, material, data...) in world.objects order — lets tests compare ingest results
+        self.lights_log = []
 
     def __del__(self):
         try:
@@ -175,30 +179,37 @@ class OracleScene:
 
     def add_sphere(self, center, radius, mat):
         t, col, p = self._mat(mat)
+        self.objects_log.append(("sphere", mat, list(center), float(radius)))
         return self.L.orc_add_sphere(self.h, _d3(center), float(radius), t, col, p)
 
     def add_plane(self, point, normal, mat):
         t, col, p = self._mat(mat)
+        self.objects_log.append(("plane", mat, list(point), list(normal)))
         return self.L.orc_add_plane(self.h, _d3(point), _d3(normal), t, col, p)
 
     def add_box(self, mn, mx, mat):
         t, col, p = self._mat(mat)
+        self.objects_log.append(("box", mat, list(mn), list(mx)))
         return self.L.orc_add_box(self.h, _d3(mn), _d3(mx), t, col, p)
 
     def add_triangle(self, v0, v1, v2, mat):
         t, col, p = self._mat(mat)
+        self.objects_log.append(("triangle", mat, list(v0), list(v1), list(v2)))
         return self.L.orc_add_triangle(self.h, _d3(v0), _d3(v1), _d3(v2), t, col, p)
 
     def add_mesh(self, vertices, indices, mat):
         t, col, p = self._mat(mat)
         v = np.ascontiguousarray(np.asarray(vertices, dtype=np.float64).reshape(-1, 3))
         i = np.ascontiguousarray(np.asarray(indices, dtype=np.float64).reshape(-1))
+        self.objects_log.append(("mesh", mat, v.copy(), i.copy()))
         return self.L.orc_add_mesh(self.h, _ptr(v, C.c_double), v.shape[0], _ptr(i, C.c_double), i.shape[0], t, col, p)
 
     def add_point_light(self, pos, color, intensity):
+        self.lights_log.append(("point", list(pos), list(color), float(intensity)))
         self.L.orc_add_point_light(self.h, _d3(pos), _d3(color), float(intensity))
 
     def add_directional_light(self, direction, color, intensity):
+        self.lights_log.append(("directional", list(direction), list(color), float(intensity)))
         self.L.orc_add_directional_light(self.h, _d3(direction), _d3(color), float(intensity))
 
     def set_camera(self, look_from, look_at, vup, vfov, aspect, aperture, focus_dist, type_str="perspective"):
@@ -220,6 +231,7 @@ class OracleScene:
     def set_background(self, kind: str, color=(0.1, 0.1, 0.1), intensity=1.0):
         self.bg_kind = kind if kind in BG else "gradient"
         self.sky_intensity = float(intensity)
+        self.solid_color = tuple(float(c) for c in color)
         self.L.orc_set_background(self.h, BG[self.bg_kind], _d3(color), float(intensity))
 
     def set_perm(self, perm256):
@@ -234,6 +246,9 @@ class OracleScene:
 
     def object_count(self):
         return self.L.orc_object_count(self.h)
+
+    def mesh_triangle_count(self, obj):
+        return self.L.orc_mesh_triangle_count(self.h, obj)
 
     def primary_aov(self, width, height):
         n = width * height
