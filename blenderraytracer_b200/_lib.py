@@ -64,7 +64,7 @@ class brt_scene_info(C.Structure):
     _fields_ = [("n_objects", C.c_int32), ("n_materials", C.c_int32), ("n_lights", C.c_int32),
                 ("n_spheres", C.c_int32), ("n_planes", C.c_int32), ("n_boxes", C.c_int32),
                 ("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("bvh_depth", C.c_int32), ("_pad", C.c_int32),
-                ("bvh_build_ms", C.c_double), ("upload_ms", C.c_double)]
+                ("bvh_build_ms", C.c_double), ("upload_ms", C.c_double), ("upload_bytes", C.c_int64)]
 
 
 class brt_stats(C.Structure):
@@ -101,6 +101,12 @@ SIGNATURES = {
     "brt_resolve_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "brt_reduce_resolve_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "brt_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "brt_shared_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "brt_shared_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "brt_shared_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "brt_shared_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "brt_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "brt_device_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
     "brt_primary_aov_f32": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "brt_primary_aov_f64": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "brt_eval_background": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_float)]),

@@ -277,6 +277,8 @@ static int upload_scene(brt_ctx* ctx) {
     inf.n_spheres = d.nSph; inf.n_planes = d.nPln; inf.n_boxes = d.nBox; inf.n_triangles = d.nTri;
     inf.n_bvh_nodes = br.nNodes; inf.bvh_depth = br.depth; inf.bvh_build_ms = br.buildMs;
     inf.upload_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    inf.upload_bytes = (int64_t)((sph.size() + pln.size() + box.size() + tri.size() + mat.size() + lights.size()) * sizeof(float4) +
+                                 meta.size() * sizeof(int4) + matType.size() * sizeof(int));
     ctx->sceneDirty = false;
     return BRT_OK;
 }
@@ -496,6 +498,60 @@ int brt_reduce_resolve_peers(brt_ctx* ctx, const float* const* d_peer_accum, int
     CK(launch_reduce_resolve(pp, (const float4* const*)d_peer_accum, n_peers, (uchar4*)d_rgba8_root, (float4*)d_float_data_root,
                              row_begin, row_end, ctx->stream));
     ctx->stats.launches += 1;
+    return BRT_OK;
+}
+
+int brt_shared_alloc(brt_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]) {
+    if (!ctx || !d_ptr || !handle || bytes == 0) return BRT_E_INVALID;
+    NEED_GPU();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(ctx, e, "cudaIpcGetMemHandle"); }
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return BRT_OK;
+}
+int brt_shared_free(brt_ctx* ctx, void* d_ptr) {
+    if (!ctx) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(d_ptr));
+    return BRT_OK;
+}
+int brt_shared_open(brt_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+    if (!ctx || !handle || !d_ptr) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BRT_OK;
+}
+int brt_shared_close(brt_ctx* ctx, void* d_ptr) {
+    if (!ctx) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return BRT_OK;
+}
+int brt_device_memset(brt_ctx* ctx, void* d_ptr, int value, size_t bytes) {
+    if (!ctx || !d_ptr) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(d_ptr, value, bytes, ctx->stream));
+    return BRT_OK;
+}
+
+int brt_copy_to_host(brt_ctx* ctx, void* host_dst, const void* d_src, size_t bytes) {
+    if (!ctx || !host_dst || !d_src) return BRT_E_INVALID;
+    NEED_GPU();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return BRT_OK;
 }
 

@@ -397,6 +397,30 @@ class RayTracer:
         tris = np.ctypeslib.as_array(d.mesh_triangles, shape=(n, 9)).copy() if n else np.zeros((0, 9))
         return dict(objects=objs, materials=mats, lights=lights, mesh_triangles=tris)
 
+    def sceneFlatDesc(self):
+        """-> (brt_scene_desc, keepalive): a caller-owned host copy of the ingested scene, in the form
+        brt_scene_set_flat takes (what the JS shim builds from a live World)."""
+        d = L.brt_scene_desc()
+        L.check(self._ctx, self._L.brt_scene_get_flat(self._ctx, C.byref(d)))
+        objs = (L.brt_object * max(1, d.n_objects))()
+        mats = (L.brt_material * max(1, d.n_materials))()
+        lights = (L.brt_light * max(1, d.n_lights))()
+        C.memmove(objs, d.objects, C.sizeof(L.brt_object) * d.n_objects)
+        C.memmove(mats, d.materials, C.sizeof(L.brt_material) * d.n_materials)
+        C.memmove(lights, d.lights, C.sizeof(L.brt_light) * d.n_lights)
+        n = int(d.n_mesh_triangles)
+        tris = np.ctypeslib.as_array(d.mesh_triangles, shape=(n, 9)).copy() if n else np.zeros((0, 9))
+        out = L.brt_scene_desc()
+        out.objects, out.n_objects = objs, d.n_objects
+        out.materials, out.n_materials = mats, d.n_materials
+        out.lights, out.n_lights = lights, d.n_lights
+        out.mesh_triangles, out.n_mesh_triangles = tris.ctypes.data_as(C.POINTER(C.c_double)), n
+        return out, (objs, mats, lights, tris)
+
+    def setSceneFlat(self, desc_keep):
+        """brt_scene_set_flat with a (desc, keepalive) pair from sceneFlatDesc() / World.flatten()."""
+        L.check(self._ctx, self._L.brt_scene_set_flat(self._ctx, C.byref(desc_keep[0])))
+
     def sceneInfo(self) -> dict:
         s = L.brt_scene_info()
         L.check(self._ctx, self._L.brt_scene_info_get(self._ctx, C.byref(s)))
@@ -457,6 +481,29 @@ class RayTracer:
         L.check(self._ctx, self._L.brt_reduce_resolve_peers(self._ctx, arr, len(peer_ptrs), int(row_begin), int(row_end),
                                                             C.c_void_p(int(d_rgba_root_ptr)),
                                                             C.c_void_p(int(d_float_root_ptr)) if d_float_root_ptr else None))
+
+    def sharedAlloc(self, nbytes):
+        """-> (device pointer, 64-byte CUDA IPC handle) of a library-owned buffer other ranks can map."""
+        p, h = C.c_void_p(), C.create_string_buffer(64)
+        L.check(self._ctx, self._L.brt_shared_alloc(self._ctx, int(nbytes), C.byref(p), h))
+        return p.value, h.raw
+
+    def sharedOpen(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        L.check(self._ctx, self._L.brt_shared_open(self._ctx, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def sharedClose(self, ptr):
+        L.check(self._ctx, self._L.brt_shared_close(self._ctx, C.c_void_p(int(ptr))))
+
+    def sharedFree(self, ptr):
+        L.check(self._ctx, self._L.brt_shared_free(self._ctx, C.c_void_p(int(ptr))))
+
+    def deviceMemset(self, ptr, value, nbytes):
+        L.check(self._ctx, self._L.brt_device_memset(self._ctx, C.c_void_p(int(ptr)), int(value), int(nbytes)))
+
+    def copyToHost(self, host_ptr, dev_ptr, nbytes):
+        L.check(self._ctx, self._L.brt_copy_to_host(self._ctx, C.c_void_p(int(host_ptr)), C.c_void_p(int(dev_ptr)), int(nbytes)))
 
     def synchronize(self):
         L.check(self._ctx, self._L.brt_stream_synchronize(self._ctx))

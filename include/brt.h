@@ -140,6 +140,7 @@ typedef struct brt_scene_info {
     int32_t bvh_depth, _pad;
     double bvh_build_ms;         /* device time of the LBVH build (Morton, radix sort, Karras, refit) */
     double upload_ms;
+    int64_t upload_bytes;        /* host -> device bytes of the flattened SoA scene (primitives, meta, materials, lights) */
 } brt_scene_info;
 
 typedef struct brt_stats {
@@ -213,6 +214,17 @@ int brt_resolve_device(brt_ctx* ctx, const float* d_accum, uint8_t* d_rgba8, flo
 int brt_reduce_resolve_peers(brt_ctx* ctx, const float* const* d_peer_accum, int n_peers, int row_begin, int row_end,
                              uint8_t* d_rgba8_root, float* d_float_data_root);
 int brt_stream_synchronize(brt_ctx* ctx);
+/* Buffers for the cross-process (one process per GPU) form of the fused reduce: cudaMalloc'd by the library so that a
+ * CUDA IPC handle (64 opaque bytes, sent to the peers by the caller, e.g. torch.distributed.all_gather_object) names
+ * them.  brt_shared_open maps a peer's buffer into this process (NVLink peer access); close before the owner frees. */
+int brt_shared_alloc(brt_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]);
+int brt_shared_free(brt_ctx* ctx, void* d_ptr);
+int brt_shared_open(brt_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+int brt_shared_close(brt_ctx* ctx, void* d_ptr);
+/* cudaMemsetAsync on the ctx stream (zeroing an accumulation buffer between renders). */
+int brt_device_memset(brt_ctx* ctx, void* d_ptr, int value, size_t bytes);
+/* Blocking device -> host copy on the ctx stream (reading back a brt_shared_alloc buffer). */
+int brt_copy_to_host(brt_ctx* ctx, void* host_dst, const void* d_src, size_t bytes);
 
 /* ---- parity AOVs (north star: primary-hit IDs bit-exact, t / normal within 1e-5) ------------------------ */
 /* Primary visibility at pixel centres with lens offset 0 (ray-tracer.js:144-147, camera.js:45-49, world.js:20-33).

@@ -637,6 +637,7 @@ struct RenderParams {
     double denoiseStrength;
     uint64_t seed;
     int32_t directLighting;   // extension, default 0 = reference behaviour
+    int32_t sampleBegin;      // first global sample index (0 = reference loop); lets tests restate a multi-GPU spp split
 };
 
 struct Scene {
@@ -708,7 +709,7 @@ void renderPixel(const Scene& sc, const RenderParams& rp, int i, int j,
     int sampleCount = rp.antiAliasing == 0 ? 1 : rp.samples;                           // :201
     uint32_t pix = (uint32_t)((rp.height - 1 - j) * rp.width + i);
     for (int s = 0; s < sampleCount; s++) {
-        Philox g(rp.seed, pix, (uint32_t)s);
+        Philox g(rp.seed, pix, (uint32_t)(s + rp.sampleBegin));
         double u, v;
         getAntiAliasSample(rp, i, j, g, u, v);
         Ray ray = sc.camera.getRay(u, v, g);

@@ -49,6 +49,7 @@ class _RenderParams(C.Structure):
         ("denoiseStrength", C.c_double),
         ("seed", C.c_uint64),
         ("directLighting", C.c_int32),
+        ("sampleBegin", C.c_int32),
     ]
 
 
@@ -609,6 +610,7 @@ class OracleRayTracer:
         rp.denoiseStrength = float(self.denoiseStrength)
         rp.seed = self.seed
         rp.directLighting = 1 if self.directLighting else 0
+        rp.sampleBegin = int(getattr(self, "sampleBegin", 0))
         return rp
 
     def render(self, onProgress=None, rect=None):                      # :166-281

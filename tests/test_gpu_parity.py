@@ -1,0 +1,529 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI (ctypes binding of include/brt.h), against the
+float64 oracle on the same seeded inputs, against the committed golden vectors, and — at BASELINE.json's full sizes —
+through size-independent properties.  Gates G2–G6 of SURVEY.md §8(c).
+
+Tolerances (north star): primary-hit object / triangle IDs bit-exact; hit distance and normal within 1e-5 relative
+(fp32 vs float64); converged images within a stated RMSE of the reference renderer (here: 1.5x the oracle's own
+seed-to-seed noise floor, plus a per-channel bias bound).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_scene  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def brt():
+    import blenderraytracer_b200 as b
+    return b
+
+
+def _pair(brt, scene, W, H, seed=3, threads=8, **settings):
+    from oracle.oracle import OracleRayTracer
+    rt = brt.RayTracer(W, H, seed=seed)
+    assert rt.loadFromJSON(scene)
+    orc = OracleRayTracer(W, H, seed=seed, threads=threads)
+    assert orc.loadFromJSON(scene)
+    if settings:
+        rt.updateRenderSettings(dict(settings))
+        orc.updateRenderSettings(dict(settings))
+    return rt, orc
+
+
+def _scenes():
+    from tools import gen_scenes
+    return {
+        "sample_scene": (load_scene("sample_scene.json"), 600, 400),
+        "sample_mesh": (load_scene("sample_mesh.json"), 1280, 720),
+        "c3_spheres": (gen_scenes.random_spheres(), 480, 270),
+        "c3_ground_sphere": (gen_scenes.random_spheres(ground="sphere", grid=4), 320, 180),
+        "c4_cornell": (gen_scenes.cornell("hdri"), 480, 270),
+        "c5_terrain_small": (gen_scenes.terrain(quads=24, extent=200.0), 320, 180),
+    }
+
+
+# ---------------------------------------------------------------------------------------------- RNG
+def test_philox_stream_matches_oracle(brt):
+    import ctypes as C
+    from oracle.oracle import lib
+    rt = brt.RayTracer(8, 8, seed=0x1234_5678_9ABC_DEF0)
+    for pixel, sample in ((0, 0), (5, 9), (2 ** 31 + 7, 4095)):
+        out = (C.c_double * 64)()
+        lib().orc_rng_stream(rt.seed, pixel, sample, 64, out)
+        np.testing.assert_array_equal(np.array(out[:], dtype=np.float32), rt.rngStream(pixel, sample, 64))
+
+
+# ---------------------------------------------------------------------------------------------- G2 primary visibility
+@pytest.mark.parametrize("name", ["sample_scene", "sample_mesh", "c3_spheres", "c3_ground_sphere", "c4_cornell", "c5_terrain_small"])
+def test_primary_aov_f64_bit_exact(brt, name):
+    """The float64, FMA-free kernel reproduces the oracle bit for bit: IDs, t, normal, frontFace."""
+    scene, W, H = _scenes()[name]
+    rt, orc = _pair(brt, scene, W, H)
+    a, o = rt.primaryAOV(64), orc.primary_aov()
+    assert np.array_equal(a["obj_id"], o["obj_id"])
+    assert np.array_equal(a["tri_id"], o["tri_id"])
+    assert np.array_equal(a["t"], o["t"])
+    assert np.array_equal(a["normal"], o["normal"])
+    assert np.array_equal(a["front_face"], o["front_face"])
+
+
+@pytest.mark.parametrize("accel", ["brute", "bvh"])
+@pytest.mark.parametrize("name", ["sample_scene", "sample_mesh", "c3_spheres", "c3_ground_sphere", "c4_cornell", "c5_terrain_small"])
+def test_primary_aov_f32(brt, name, accel):
+    """The render path's fp32 intersection code: IDs equal to the float64 reference except on a bounded number of
+    silhouette pixels (reported), t and normal within 1e-5 relative where the IDs agree."""
+    scene, W, H = _scenes()[name]
+    rt, orc = _pair(brt, scene, W, H)
+    rt.accel = accel
+    a, o = rt.primaryAOV(32), orc.primary_aov()
+    mism = (a["obj_id"] != o["obj_id"]) | (a["tri_id"] != o["tri_id"])
+    assert mism.mean() <= 2e-4, f"{int(mism.sum())} of {mism.size} primary IDs differ"
+    ok = ~mism & (o["obj_id"] >= 0)
+    rel = np.abs(a["t"][ok].astype(np.float64) - o["t"][ok]) / o["t"][ok]
+    assert rel.max() <= 1e-5, f"max relative t error {rel.max():.3e}"
+    dn = np.abs(a["normal"][ok].astype(np.float64) - o["normal"][ok]).max()
+    assert dn <= 1e-5, f"max normal error {dn:.3e}"
+    assert np.array_equal(a["front_face"][ok], o["front_face"][ok])
+    miss = ~mism & (o["obj_id"] < 0)
+    assert np.all(np.isinf(a["t"][miss]))
+
+
+def test_golden_primary_hits(brt, kat):
+    """tests/golden/kat.json KAT-B rows against both GPU AOV kernels."""
+    for name, fx, W, H in (("sample_scene_600x400", "sample_scene.json", 600, 400), ("sample_mesh_1280x720", "sample_mesh.json", 1280, 720)):
+        rt = brt.RayTracer(W, H)
+        assert rt.loadFromJSON(load_scene(fx))
+        a64, a32 = rt.primaryAOV(64), rt.primaryAOV(32)
+        for row in kat["primary"][name]:
+            r, i = H - 1 - row["j"], row["i"]
+            assert a64["obj_id"][r, i] == row["obj"] == a32["obj_id"][r, i]
+            assert a64["tri_id"][r, i] == row["tri"] == a32["tri_id"][r, i]
+            assert a64["t"][r, i] == row["t"]
+            assert abs(a32["t"][r, i] - row["t"]) <= 1e-5 * row["t"]
+            np.testing.assert_allclose(a32["normal"][r, i], row["normal"], atol=1e-5)
+            assert bool(a64["front_face"][r, i]) == row["front"] == bool(a32["front_face"][r, i])
+
+
+def test_golden_camera(brt, kat):
+    for name, fx, W, H in (("sample_scene", "sample_scene.json", 600, 400), ("sample_mesh", "sample_mesh.json", 1280, 720)):
+        rt = brt.RayTracer(W, H)
+        assert rt.loadFromJSON(load_scene(fx))
+        cam = rt.camera
+        for key in ("w", "u", "v", "horizontal", "vertical", "lowerLeftCorner", "origin"):
+            np.testing.assert_allclose(cam[key], kat["camera"][name][key], rtol=0, atol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------- G5 BVH == brute force
+def _tie_scene(seed=7):
+    """Duplicate, coplanar and overlapping geometry: exercises the first-object / last-triangle tie rules."""
+    rng = np.random.default_rng(seed)
+    objs = []
+    lam = lambda c: dict(type="lambertian", color=c)
+    for k in range(40):
+        c = rng.uniform(-3, 3, 3).round(3).tolist()
+        r = float(rng.uniform(0.2, 0.7).round(3))
+        objs.append(dict(type="sphere", center=c, radius=r, material=lam([0.5, 0.5, 0.5])))
+        if k % 4 == 0:
+            objs.append(dict(type="sphere", center=c, radius=r, material=dict(type="metal", color=[0.9, 0.9, 0.9], roughness=0.1)))   # exact duplicate
+    for k in range(10):
+        mn = rng.uniform(-3, 2, 3).round(2)
+        objs.append(dict(type="box", min=mn.tolist(), max=(mn + rng.uniform(0.3, 1.0, 3).round(2)).tolist(), material=lam([0.2, 0.6, 0.3])))
+    objs.append(dict(type="box", min=[-1, -1, -1], max=[1, 1, 1], material=lam([0.7, 0.2, 0.2])))
+    objs.append(dict(type="box", min=[-1, -1, -1], max=[1, 1, 1], material=lam([0.2, 0.2, 0.7])))      # duplicate box
+    # a mesh whose triangles are listed twice (second copy must win inside the mesh) + coplanar overlapping quads
+    verts = [[-2, -2, 2.5], [2, -2, 2.5], [2, 2, 2.5], [-2, 2, 2.5], [-1, -1, 2.5], [3, -1, 2.5], [3, 3, 2.5]]
+    idx = [0, 1, 2, 0, 2, 3, 0, 1, 2, 0, 2, 3, 4, 5, 6]
+    objs.append(dict(type="mesh", vertices=verts, indices=idx, material=lam([0.8, 0.8, 0.1])))
+    objs.append(dict(type="triangle", v0=[-2, -2, 2.5], v1=[2, -2, 2.5], v2=[2, 2, 2.5], material=lam([0.1, 0.8, 0.8])))
+    objs.append(dict(type="plane", point=[0, -3, 0], normal=[0, 1, 0], material=lam([0.5, 0.5, 0.5])))
+    return dict(objects=objs, camera=dict(position=[0.5, 1.0, 9.0], lookAt=[0, 0, 0], fov=50, aspect=1.5, aperture=0.0, focusDist=9.0),
+                background=dict(type="gradient"))
+
+
+@pytest.mark.parametrize("name", ["ties", "c3_spheres", "c4_cornell", "c5_terrain_small", "sample_mesh"])
+def test_bvh_is_invisible(brt, name):
+    """The LBVH must not change results: AOVs and (same Philox stream) whole images equal the brute-force loops bit for bit."""
+    scene, W, H = (_tie_scene(), 360, 240) if name == "ties" else _scenes()[name]
+    rt = brt.RayTracer(W, H, seed=5)
+    assert rt.loadFromJSON(scene)
+    assert rt.sceneInfo()["n_bvh_nodes"] > 0
+    out = {}
+    for accel in ("brute", "bvh"):
+        rt.accel = accel
+        a = rt.primaryAOV(32)
+        rt.updateRenderSettings(dict(samples=4, maxBounces=6))
+        rt.sampler = "reference"
+        img = rt.render(want_linear=True)
+        out[accel] = (a, img.copy(), rt.linearMean.copy())
+    for key in ("obj_id", "tri_id", "t", "normal", "front_face"):
+        assert np.array_equal(out["brute"][0][key], out["bvh"][0][key]), key
+    assert np.array_equal(out["brute"][1], out["bvh"][1])
+    assert np.array_equal(out["brute"][2], out["bvh"][2])
+
+
+def test_tie_rules_match_oracle(brt):
+    scene = _tie_scene()
+    rt, orc = _pair(brt, scene, 360, 240)
+    a64, o = rt.primaryAOV(64), orc.primary_aov()
+    assert np.array_equal(a64["obj_id"], o["obj_id"]) and np.array_equal(a64["tri_id"], o["tri_id"])
+    for accel in ("brute", "bvh"):
+        rt.accel = accel
+        a = rt.primaryAOV(32)
+        mism = (a["obj_id"] != o["obj_id"]) | (a["tri_id"] != o["tri_id"])
+        assert mism.mean() <= 5e-4, (accel, int(mism.sum()))
+
+
+# ---------------------------------------------------------------------------------------------- G3 deterministic scenes
+@pytest.mark.parametrize("depth", [1, 2, 3, 5, 16])
+def test_deterministic_scene_full_image(brt, kat, depth):
+    """Mirror metal + emissive plane + gradient sky (KAT-D): no RNG influence, so the whole image is comparable at 1e-5
+    (away from fp32 silhouette flips) and RGBA8 within 1 LSB; sweeps depth to pin the <=-depth-intersections rule."""
+    D = kat["deterministic"]
+    W, H = D["width"], D["height"]
+    rt, orc = _pair(brt, D["scene"], W, H, seed=9, maxBounces=depth, samples=1, antiAliasing="none")
+    img = rt.render(want_linear=True)
+    ref = orc.render()
+    lin, rl = rt.linearMean[..., :3].astype(np.float64), orc.linear[..., :3]
+    err = np.abs(lin - rl) / np.maximum(np.abs(rl), 1e-3)
+    bad = err.max(axis=-1) > 1e-5
+    assert bad.mean() <= 2e-3, f"{int(bad.sum())} pixels beyond 1e-5 (silhouette flips expected to be ~0.1%)"
+    d = np.abs(img.astype(int) - ref.astype(int)).max(axis=-1)
+    assert (d[~bad] <= 1).all()
+    if depth == D["depth"]:
+        for row in D["pixels"]:
+            r, i = H - 1 - row["j"], row["i"]
+            np.testing.assert_allclose(lin[r, i], row["linear"], rtol=1e-5)
+            assert np.abs(img[r, i].astype(int) - np.array(row["rgba8"])).max() <= 1
+
+
+def test_max_depth_zero_is_black(brt, sample_scene):
+    rt = brt.RayTracer(64, 48)
+    assert rt.loadFromJSON(sample_scene)
+    rt.maxBounces = 0                                   # updateRenderSettings would turn 0 into 5 (`||`)
+    img = rt.render()
+    assert np.all(img[..., :3] == 0) and np.all(img[..., 3] == 255)
+
+
+# ---------------------------------------------------------------------------------------------- same stream, sample for sample
+@pytest.mark.parametrize("name,W,H", [("sample_scene", 300, 200), ("sample_mesh", 320, 180), ("c3_spheres", 240, 135), ("c4_cornell", 240, 135)])
+def test_reference_sampler_tracks_oracle_sample_for_sample(brt, name, W, H):
+    """BRT_SAMPLER_REFERENCE consumes the oracle's Philox stream in the reference's draw order: every path is the same
+    path, so images agree except where fp32 flips a discrete decision (silhouettes, Russian-doll glass)."""
+    scene = _scenes()[name][0]
+    rt, orc = _pair(brt, scene, W, H, seed=11, samples=8, maxBounces=8)
+    rt.sampler = "reference"
+    img = rt.render(want_linear=True)
+    ref = orc.render()
+    d = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=-1)
+    assert (d <= 2).mean() >= 0.97, f"only {(d <= 2).mean():.4f} of pixels within 2 LSB"
+    err = np.abs(rt.linearMean[..., :3] - orc.linear[..., :3])
+    assert np.median(err) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- G4 statistical parity
+def _stat_gate(brt, scene, W, H, spp, depth, **extra):
+    from oracle.oracle import OracleRayTracer
+    rt, orc = _pair(brt, scene, W, H, seed=21, samples=spp, maxBounces=depth, **extra)
+    rt.sampler = "fast"
+    rt.render()
+    orc.render()
+    orc2 = OracleRayTracer(W, H, seed=22, threads=8)
+    assert orc2.loadFromJSON(scene)
+    orc2.updateRenderSettings(dict(samples=spp, maxBounces=depth, **extra))
+    orc2.render()
+    g, a, b = rt.floatData[..., :3].astype(np.float64), orc.floatData[..., :3].astype(np.float64), orc2.floatData[..., :3].astype(np.float64)
+    rmse = np.sqrt(np.mean((g - a) ** 2))
+    floor = np.sqrt(np.mean((b - a) ** 2))
+    bias = (g - a).mean(axis=(0, 1))
+    bias_floor = np.abs((b - a).mean(axis=(0, 1)))
+    return rmse, floor, bias, bias_floor
+
+
+@pytest.mark.parametrize("name,W,H,spp,depth", [("sample_scene", 300, 200, 32, 10), ("sample_mesh", 320, 180, 32, 10),
+                                                ("c3_spheres", 192, 108, 16, 10), ("c4_cornell", 192, 108, 32, 16)])
+def test_fast_sampler_statistical_parity(brt, name, W, H, spp, depth):
+    """Independent random numbers (direct-inversion sampling, one Philox block per bounce): RMSE on tone-mapped [0,1] values
+    against the oracle <= 1.5x the oracle's own seed-to-seed RMSE, and |mean signed error| <= 2e-3 per channel."""
+    rmse, floor, bias, bias_floor = _stat_gate(brt, _scenes()[name][0], W, H, spp, depth)
+    assert rmse <= 1.5 * floor + 1e-4, (rmse, floor)
+    assert np.all(np.abs(bias) <= 2e-3 + 3 * bias_floor), (bias, bias_floor)
+
+
+@pytest.mark.parametrize("aa", ["stochastic", "none", "weird"])
+def test_antialias_modes(brt, sample_scene, aa):
+    rmse, floor, bias, _ = _stat_gate(brt, sample_scene, 150, 100, 16, 6, antiAliasing=aa)
+    assert rmse <= 1.5 * floor + 1e-4
+    assert np.all(np.abs(bias) <= 4e-3)
+
+
+def test_orthographic_and_other_camera_types(brt, sample_scene):
+    for ty in ("orthographic", "fisheye"):
+        sc = json.loads(json.dumps(sample_scene))
+        sc["camera"]["type"] = ty
+        rt, orc = _pair(brt, sc, 150, 100)
+        a, o = rt.primaryAOV(64), orc.primary_aov()
+        assert np.array_equal(a["obj_id"], o["obj_id"]) and np.array_equal(a["t"], o["t"]), ty
+        a32 = rt.primaryAOV(32)
+        assert (a32["obj_id"] != o["obj_id"]).mean() <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- backgrounds
+@pytest.mark.parametrize("kind", ["gradient", "solid", "hdri", "procedural_sky"])
+def test_backgrounds_match_oracle(brt, kind):
+    from oracle.oracle import OracleScene, make_perm
+    rng = np.random.default_rng(3)
+    dirs = rng.normal(size=(4096, 3)) * rng.uniform(0.1, 10, size=(4096, 1))      # un-normalised, like scattered rays
+    dirs = np.concatenate([dirs, [[0, 1, 0], [0, -1, 0], [1, 0, 0], [0.3, 0.6, 0.8], [-0.3, 0.6, -0.5]]])
+    rt = brt.RayTracer(8, 8, perm_seed=5)
+    rt._bg = (kind, (0.2, 0.4, 0.6), 1.7)
+    rt._push_background()
+    got = rt.evalBackground(dirs)
+    sc = OracleScene()
+    sc.set_perm(make_perm(5))
+    sc.set_background(kind, (0.2, 0.4, 0.6), 1.7)
+    want = np.array([sc.background(d) for d in dirs])
+    # fp32 evaluation of float64 formulas; the sun terms (pow 512, thresholded disk) amplify direction rounding
+    tol = 2e-3 if kind in ("procedural_sky", "hdri") else 1e-5
+    close = np.abs(got - want) <= tol * np.maximum(1.0, np.abs(want))
+    assert close.mean() >= 0.999, f"{(~close).sum()} of {close.size} background values differ"
+    if kind in ("gradient", "solid"):
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_golden_background_scalars(brt, kat):
+    rt = brt.RayTracer(8, 8)
+    rt.updateBackground("hdri", 1.0)
+    s = kat["scalars"]["hdri"]
+    got = rt.evalBackground([[0, 1, 0], [1, 0, 0], [0, -1, 0]])
+    np.testing.assert_allclose(got, [s["0,1,0"], s["1,0,0"], s["0,-1,0"]], rtol=1e-5)
+    rt.updateBackground("gradient", 1.0)
+    np.testing.assert_allclose(rt.evalBackground([[0, 1, 0]])[0], kat["scalars"]["sky_up"], rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- post-processing
+@pytest.mark.parametrize("tonemap", ["reinhard", "aces", "linear"])
+@pytest.mark.parametrize("denoise", [False, True])
+def test_postprocess_matches_oracle(brt, tonemap, denoise):
+    """resolve / denoise kernels on a host linear image vs post-processor.js restated in the oracle: RGBA8 within 1 LSB
+    (fp64 pow's last ulp across floor), floatData within 1e-6."""
+    import ctypes as C
+    from oracle.oracle import lib
+    L = lib()
+    W, H = 97, 61
+    rng = np.random.default_rng(8)
+    lin = np.zeros((H, W, 4), np.float32)
+    lin[..., :3] = rng.gamma(0.7, 1.2, size=(H, W, 3)).astype(np.float32)
+    lin[0, 0, :3] = [0, 1, 1e-8]
+    lin[..., 3] = 1
+    rt = brt.RayTracer(W, H)
+    rt.updateRenderSettings(dict(toneMapping=tonemap, exposure=1.3, gamma=2.4, denoising=denoise, denoiseStrength=0.6))
+    got = rt.postprocess(lin)
+    want_f = np.zeros((H, W, 4), np.float32)
+    out3 = (C.c_double * 3)()
+    tm = {"reinhard": 0, "aces": 1, "linear": 2}[tonemap]
+    for y in range(H):
+        for x in range(W):
+            c = (C.c_double * 3)(*[float(v) for v in lin[y, x, :3]])
+            L.orc_tonemap(tm, 1.3, c, out3)
+            c2 = (C.c_double * 3)(*out3)
+            L.orc_gamma(2.4, c2, out3)
+            want_f[y, x, :3] = out3[:]
+            want_f[y, x, 3] = 1
+    if denoise:
+        dn = np.empty_like(want_f)
+        L.orc_denoise(want_f.ctypes.data_as(C.POINTER(C.c_float)), W, H, 0.6, dn.ctypes.data_as(C.POINTER(C.c_float)))
+        want_img = np.empty((H, W, 4), np.uint8)
+        L.orc_quantize_image(dn.ctypes.data_as(C.POINTER(C.c_float)), W, H, want_img.ctypes.data_as(C.POINTER(C.c_uint8)))
+    else:
+        want_img = np.empty((H, W, 4), np.uint8)
+        L.orc_quantize_image(want_f.ctypes.data_as(C.POINTER(C.c_float)), W, H, want_img.ctypes.data_as(C.POINTER(C.c_uint8)))
+    np.testing.assert_allclose(rt.floatData, want_f, rtol=2e-6, atol=1e-7)
+    d = np.abs(got.astype(int) - want_img.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() <= 1e-3
+    assert np.all(got[..., 3] == 255)
+
+
+def test_golden_tonemap_scalars(brt, kat):
+    rt = brt.RayTracer(2, 1)
+    lin = np.ones((1, 2, 4), np.float32)
+    rt.updateRenderSettings(dict(toneMapping="reinhard", gamma=2.2, exposure=1.0))
+    assert rt.postprocess(lin)[0, 0, 0] == kat["scalars"]["reinhard_1_u8"] == 186
+    rt.updateRenderSettings(dict(toneMapping="aces", gamma=1.0000001, exposure=1.0))
+    rt.postprocess(lin)
+    assert rt.floatData[0, 0, 0] == pytest.approx(kat["scalars"]["aces_1"], rel=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- G6 sample partitions
+def test_spp_split_is_partition_invariant(brt, sample_mesh):
+    """The RNG is keyed by the global sample index: accumulating [0,5) + [5,16) equals [0,16) up to fp32 summation order,
+    and resolving the split sums gives the same RGBA8 (within 1 LSB)."""
+    import torch
+    W, H, spp = 160, 90, 16
+    rt = brt.RayTracer(W, H, seed=4)
+    assert rt.loadFromJSON(sample_mesh)
+    rt.updateRenderSettings(dict(samples=spp, maxBounces=8))
+    rt.setStream(torch.cuda.current_stream().cuda_stream)
+    rt._push_params()
+    a = torch.zeros((H, W, 4), device="cuda")
+    b = torch.zeros((H, W, 4), device="cuda")
+    rt.renderAccumulate(a.data_ptr(), 0, spp)
+    rt.renderAccumulate(b.data_ptr(), 0, 5)
+    rt.renderAccumulate(b.data_ptr(), 5, spp - 5)
+    rt.synchronize()
+    assert torch.all(a[..., 3] == spp) and torch.all(b[..., 3] == spp)
+    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+    ia = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    ib = torch.zeros_like(ia)
+    rt.resolveDevice(a.data_ptr(), ia.data_ptr())
+    rt.resolveDevice(b.data_ptr(), ib.data_ptr())
+    rt.synchronize()
+    assert (ia.int() - ib.int()).abs().max().item() <= 1
+    # and the blocking host API gives the same picture as accumulate + resolve
+    img = rt.render()
+    assert np.abs(img.astype(int) - ia.cpu().numpy().astype(int)).max() <= 1
+
+
+def test_fused_peer_reduce_resolve_single_gpu(brt, sample_scene):
+    """brt_reduce_resolve_peers with N 'peer' buffers that all live on this GPU (N ranks emulated as one kernel over all
+    ranks' data): equals resolve(sum of the buffers)."""
+    import torch
+    from blenderraytracer_b200.distributed import sample_range, row_stripe
+    W, H, spp, N = 120, 80, 12, 3
+    rt = brt.RayTracer(W, H, seed=6)
+    assert rt.loadFromJSON(sample_scene)
+    rt.updateRenderSettings(dict(samples=spp, maxBounces=6))
+    rt.setStream(torch.cuda.current_stream().cuda_stream)
+    rt._push_params()
+    parts = [torch.zeros((H, W, 4), device="cuda") for _ in range(N)]
+    for r, p in enumerate(parts):
+        b, c = sample_range(spp, r, N)
+        rt.renderAccumulate(p.data_ptr(), b, c)
+    fused = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    for r in range(N):
+        r0, r1 = row_stripe(H, r, N)
+        rt.reduceResolvePeers([p.data_ptr() for p in parts], r0, r1, fused.data_ptr())
+    total = parts[0] + parts[1] + parts[2]
+    plain = torch.zeros_like(fused)
+    rt.resolveDevice(total.data_ptr(), plain.data_ptr())
+    rt.synchronize()
+    assert torch.equal(fused, plain)
+
+
+# ---------------------------------------------------------------------------------------------- properties at full size
+def test_full_size_c3_properties(brt):
+    """BASELINE config 3 at 1920x1080 (reduced spp keeps the test short; properties do not depend on spp):
+    determinism, exact linearity in the sky intensity (x2 is exact in binary fp), radiance bounds, alpha, and
+    fp32-BVH vs float64-brute-force primary IDs over the whole frame."""
+    from tools import gen_scenes
+    W, H = 1920, 1080
+    rt = brt.RayTracer(W, H, seed=2)
+    assert rt.loadFromJSON(gen_scenes.random_spheres())
+    rt.updateRenderSettings(dict(samples=4, maxBounces=10))
+    img1 = rt.render(want_linear=True)
+    lin1 = rt.linearMean.copy()
+    img2 = rt.render(want_linear=True)
+    assert np.array_equal(img1, img2) and np.array_equal(lin1, rt.linearMean)              # idempotent / deterministic
+    rt.updateBackground("gradient", 2.0)
+    rt.render(want_linear=True)
+    assert np.array_equal(rt.linearMean[..., :3], 2.0 * lin1[..., :3])                      # linear in emitted radiance, exactly
+    assert lin1[..., :3].min() >= 0 and lin1[..., :3].max() <= 1.0 + 1e-6                   # no emitters: bounded by the sky
+    assert np.all(img1[..., 3] == 255)
+    a64, a32 = rt.primaryAOV(64), rt.primaryAOV(32)
+    mism = (a64["obj_id"] != a32["obj_id"])
+    assert mism.mean() <= 1e-4, int(mism.sum())
+    ok = ~mism & (a64["obj_id"] >= 0)
+    rel = np.abs(a32["t"][ok] - a64["t"][ok]) / a64["t"][ok]
+    assert rel.max() <= 1e-5, rel.max()
+
+
+def test_white_furnace(brt):
+    """Energy conservation: albedo-1 Lambertian / mirror / glass inside a uniform solid sky of radiance 1 returns exactly
+    radiance 1 for every path that escapes within the depth budget, and never more."""
+    objs = [dict(type="sphere", center=[x, 0, -3], radius=0.45, material=m) for x, m in (
+        (-1.0, dict(type="lambertian", color=[1, 1, 1])), (0.0, dict(type="metal", color=[1, 1, 1], roughness=0.3)),
+        (1.0, dict(type="dielectric", ior=1.5)))]
+    scene = dict(objects=objs, camera=dict(position=[0, 0, 0], lookAt=[0, 0, -3], fov=40, aspect=2.0, aperture=0.0, focusDist=3.0),
+                 background=dict(type="gradient"))
+    rt = brt.RayTracer(256, 128, seed=3)
+    assert rt.loadFromJSON(scene)
+    rt.updateBackground("solid", 10.0)                    # (0.1,0.1,0.1) * 10 = radiance 1
+    rt.updateRenderSettings(dict(samples=64, maxBounces=50, toneMapping="linear", gamma=1.0))
+    rt.render(want_linear=True)
+    lin = rt.linearMean[..., :3]
+    assert lin.max() <= 1.0 + 1e-5
+    assert lin.mean() >= 0.995                            # the only loss: rough-metal absorption below the horizon + depth cut-off
+    assert np.allclose(lin[0, 0], 1.0, atol=1e-6)
+
+
+def test_full_size_c5_bvh_build_and_aov(brt):
+    """BASELINE config 5 geometry (1,002,528 triangles): LBVH builds, traversal finds what a float64 brute-force
+    reference finds on a sparse set of pixels (the full brute-force frame is 8.3 Mpx x 1M tests — only the crop is checked)."""
+    from tools import gen_scenes
+    from oracle.oracle import OracleRayTracer
+    scene = gen_scenes.terrain()
+    W, H = 384, 216
+    rt = brt.RayTracer(W, H, seed=2)
+    assert rt.loadFromJSON(scene)
+    info = rt.sceneInfo()
+    assert info["n_triangles"] == 1002528 + 6 and info["n_bvh_nodes"] == info["n_triangles"] - 1
+    rt.accel = "bvh"
+    a32 = rt.primaryAOV(32)
+    assert (a32["obj_id"] >= 0).mean() > 0.3
+    a64 = rt.primaryAOV(64)                                # float64 brute force on the GPU: 83k px x 1M tris
+    mism = (a64["obj_id"] != a32["obj_id"]) | (a64["tri_id"] != a32["tri_id"])
+    assert mism.mean() <= 1e-3, int(mism.sum())
+    ok = ~mism & (a64["obj_id"] >= 0)
+    rel = np.abs(a32["t"][ok] - a64["t"][ok]) / a64["t"][ok]
+    assert rel.max() <= 1e-5
+    # the oracle itself on a handful of pixels (CPU brute force, 1M triangles per ray)
+    orc = OracleRayTracer(W, H, seed=2, threads=8)
+    assert orc.loadFromJSON(scene)
+    o = orc.scene.primary_aov_pixels(W, H, [(10, 200), (192, 108), (300, 150), (50, 60)]) if hasattr(orc.scene, "primary_aov_pixels") else None
+    if o is not None:
+        for (x, y), rec in o.items():
+            assert a64["obj_id"][y, x] == rec["obj_id"] and a64["tri_id"][y, x] == rec["tri_id"] and a64["t"][y, x] == rec["t"]
+
+
+# ---------------------------------------------------------------------------------------------- boundary behaviour
+def test_progress_cancel_and_errors(brt, sample_scene):
+    from blenderraytracer_b200 import _lib as L
+    rt = brt.RayTracer(200, 120, seed=1)
+    assert rt.loadFromJSON(sample_scene)
+    rt.updateRenderSettings(dict(samples=32, maxBounces=5))
+    seen = []
+    rt.render(onProgress=seen.append)
+    assert seen and seen[-1] == 1.0 and all(b >= a for a, b in zip(seen, seen[1:])) and len(seen) >= 8
+
+    def cancel_midway(f):
+        if f >= 0.25:
+            rt.cancel()
+    with pytest.raises(brt.BrtError) as ei:
+        rt.render(onProgress=cancel_midway)
+    assert ei.value.code == L.BRT_E_CANCELLED
+    assert rt.render().shape == (120, 200, 4)             # a later render starts clean (ui-controller.js:147)
+    assert rt.loadFromJSON("{not json") is False          # the reference logs and returns false (ray-tracer.js:330-333)
+    assert rt.loadFromJSON({"objects": [{"type": 5}]}) is False   # objData.type.toLowerCase throws
+    assert rt.render().shape == (120, 200, 4)             # and the previous scene is still there
+
+
+def test_direct_lighting_extension_matches_oracle(brt, sample_mesh):
+    """EXTENSION (off by default; lights.js is dead code in the reference): point / directional shadow rays.  Pinned only by
+    our own oracle's restatement of the same rule."""
+    from oracle.oracle import OracleRayTracer
+    W, H = 200, 112
+    rt, orc = _pair(brt, sample_mesh, W, H, seed=13, samples=8, maxBounces=4)
+    rt.sampler = "reference"
+    rt.directLighting = True
+    orc.directLighting = True
+    img = rt.render(want_linear=True)
+    ref = orc.render()
+    d = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=-1)
+    assert (d <= 2).mean() >= 0.97
+    rt.directLighting = False
+    off = rt.render(want_linear=True)
+    assert rt.linearMean[..., :3].mean() < orc.linear[..., :3].mean()      # lights add energy
