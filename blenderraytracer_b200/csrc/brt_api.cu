@@ -35,7 +35,7 @@ struct brt_ctx {
     brt_camera cam{}; bool haveCam = false;
     brt_render_params rp{};
     // device scene
-    DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm;
+    DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm, dPrim64;
     float4* dNodes = nullptr;
     DevScene dev{};
     bool sceneDirty = true, permDirty = true;
@@ -105,7 +105,7 @@ void brt_destroy(brt_ctx* ctx) {
     if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->dSph, &ctx->dPln, &ctx->dBox, &ctx->dTri, &ctx->dMeta, &ctx->dMat, &ctx->dMatType, &ctx->dLights, &ctx->dPerm,
+    DevBuf* bufs[] = { &ctx->dSph, &ctx->dPln, &ctx->dBox, &ctx->dTri, &ctx->dMeta, &ctx->dMat, &ctx->dMatType, &ctx->dLights, &ctx->dPerm, &ctx->dPrim64,
                        &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch,
                        &ctx->dObj64, &ctx->dTris64 };
     for (DevBuf* b : bufs) b->release();
@@ -203,6 +203,7 @@ static int upload_scene(brt_ctx* ctx) {
     std::vector<float4> sph, pln, box, tri, mat, lights;
     std::vector<int4> mSph, mPln, mBox, mTri;
     std::vector<int> matType;
+    std::vector<double> qSph, qPln, qBox, qTri;                       // float64 copies (9 per primitive) for primary-hit evaluation
     size_t nTriTotal = 0;
     for (const brt_object& o : s.objects) nTriTotal += o.type == BRT_OBJ_TRIANGLE ? 1 : o.type == BRT_OBJ_MESH ? (size_t)o.tri_count : 0;
     if (nTriTotal >= (1u << 28) || s.objects.size() >= (1u << 28)) return fail(ctx, BRT_E_INVALID, "too many primitives (limit 2^28 per type)");
@@ -213,14 +214,19 @@ static int upload_scene(brt_ctx* ctx) {
         tri.push_back(f4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], 0));
         tri.push_back(f4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0));
         mTri.push_back(make_int4(obj, m, triId, 0));
+        qTri.insert(qTri.end(), v0, v0 + 3); qTri.insert(qTri.end(), v1, v1 + 3); qTri.insert(qTri.end(), v2, v2 + 3);
+    };
+    auto push9 = [](std::vector<double>& q, const double* a, const double* b, const double* c) {
+        static const double z[3] = { 0, 0, 0 };
+        q.insert(q.end(), a, a + 3); q.insert(q.end(), b ? b : z, (b ? b : z) + 3); q.insert(q.end(), c ? c : z, (c ? c : z) + 3);
     };
     for (size_t i = 0; i < s.objects.size(); i++) {
         const brt_object& o = s.objects[i];
         int obj = (int)i;
         switch (o.type) {
-        case BRT_OBJ_SPHERE: sph.push_back(f4(o.a[0], o.a[1], o.a[2], o.b[0])); mSph.push_back(make_int4(obj, o.material, -1, 0)); break;
-        case BRT_OBJ_PLANE: pln.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); pln.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); mPln.push_back(make_int4(obj, o.material, -1, 0)); break;
-        case BRT_OBJ_BOX: box.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); box.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); mBox.push_back(make_int4(obj, o.material, -1, 0)); break;
+        case BRT_OBJ_SPHERE: sph.push_back(f4(o.a[0], o.a[1], o.a[2], o.b[0])); mSph.push_back(make_int4(obj, o.material, -1, 0)); push9(qSph, o.a, o.b, nullptr); break;
+        case BRT_OBJ_PLANE: pln.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); pln.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); mPln.push_back(make_int4(obj, o.material, -1, 0)); push9(qPln, o.b, o.a, nullptr); break;
+        case BRT_OBJ_BOX: box.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); box.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); mBox.push_back(make_int4(obj, o.material, -1, 0)); push9(qBox, o.a, o.b, nullptr); break;
         case BRT_OBJ_TRIANGLE: push_tri(o.a, o.b, o.c, obj, o.material, -1); break;
         default:
             for (int64_t t = 0; t < o.tri_count; t++) {
@@ -240,6 +246,10 @@ static int upload_scene(brt_ctx* ctx) {
     d.basePln = (int)meta.size(); meta.insert(meta.end(), mPln.begin(), mPln.end());
     d.baseBox = (int)meta.size(); meta.insert(meta.end(), mBox.begin(), mBox.end());
     d.baseTri = (int)meta.size(); meta.insert(meta.end(), mTri.begin(), mTri.end());
+    std::vector<double> prim64;
+    prim64.reserve(qSph.size() + qPln.size() + qBox.size() + qTri.size());
+    prim64.insert(prim64.end(), qSph.begin(), qSph.end()); prim64.insert(prim64.end(), qPln.begin(), qPln.end());
+    prim64.insert(prim64.end(), qBox.begin(), qBox.end()); prim64.insert(prim64.end(), qTri.begin(), qTri.end());
     d.nSph = (int)mSph.size(); d.nPln = (int)mPln.size(); d.nBox = (int)mBox.size(); d.nTri = (int)mTri.size();
     d.nLights = (int)s.lights.size();
     auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
@@ -256,10 +266,11 @@ static int upload_scene(brt_ctx* ctx) {
     CK(up(ctx->dMat, mat.data(), mat.size() * sizeof(float4)));
     CK(up(ctx->dMatType, matType.data(), matType.size() * sizeof(int)));
     CK(up(ctx->dLights, lights.data(), lights.size() * sizeof(float4)));
+    CK(up(ctx->dPrim64, prim64.data(), prim64.size() * sizeof(double)));
     CK(cudaStreamSynchronize(ctx->stream));
     d.sph = (const float4*)ctx->dSph.p; d.pln = (const float4*)ctx->dPln.p; d.box = (const float4*)ctx->dBox.p; d.tri = (const float4*)ctx->dTri.p;
     d.meta = (const int4*)ctx->dMeta.p; d.mat = (const float4*)ctx->dMat.p; d.matType = (const int*)ctx->dMatType.p;
-    d.lights = (const float4*)ctx->dLights.p;
+    d.lights = (const float4*)ctx->dLights.p; d.prim64 = (const double*)ctx->dPrim64.p;
     auto t1 = std::chrono::steady_clock::now();
     // LBVH over the bounded primitives
     if (ctx->dNodes) { cudaFree(ctx->dNodes); ctx->dNodes = nullptr; }
@@ -278,7 +289,7 @@ static int upload_scene(brt_ctx* ctx) {
     inf.n_bvh_nodes = br.nNodes; inf.bvh_depth = br.depth; inf.bvh_build_ms = br.buildMs;
     inf.upload_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     inf.upload_bytes = (int64_t)((sph.size() + pln.size() + box.size() + tri.size() + mat.size() + lights.size()) * sizeof(float4) +
-                                 meta.size() * sizeof(int4) + matType.size() * sizeof(int));
+                                 meta.size() * sizeof(int4) + matType.size() * sizeof(int) + prim64.size() * sizeof(double));
     ctx->sceneDirty = false;
     return BRT_OK;
 }
@@ -396,17 +407,15 @@ static int prepare(brt_ctx* ctx, PTParams& p) {
     p.sc = ctx->dev;
     const brt_camera& c = ctx->cam;
     DevCamera& dc = p.cam;
-    dc.ox = (float)c.origin[0]; dc.oy = (float)c.origin[1]; dc.oz = (float)c.origin[2];
-    dc.llx = (float)c.lower_left_corner[0]; dc.lly = (float)c.lower_left_corner[1]; dc.llz = (float)c.lower_left_corner[2];
-    dc.hx = (float)c.horizontal[0]; dc.hy = (float)c.horizontal[1]; dc.hz = (float)c.horizontal[2];
-    dc.vx = (float)c.vertical[0]; dc.vy = (float)c.vertical[1]; dc.vz = (float)c.vertical[2];
-    dc.ux = (float)c.u[0]; dc.uy = (float)c.u[1]; dc.uz = (float)c.u[2];
-    dc.wx = (float)c.w[0]; dc.wy = (float)c.w[1]; dc.wz = (float)c.w[2];
-    dc.vvx = (float)c.v[0]; dc.vvy = (float)c.v[1]; dc.vvz = (float)c.v[2];
-    dc.lensRadius = (float)c.lens_radius; dc.type = c.type;
+    for (int k = 0; k < 3; k++) {
+        dc.o[k] = c.origin[k]; dc.ll[k] = c.lower_left_corner[k]; dc.h[k] = c.horizontal[k]; dc.v[k] = c.vertical[k];
+        dc.cu[k] = c.u[k]; dc.cv[k] = c.v[k]; dc.cw[k] = c.w[k];
+    }
+    dc.lensRadius = c.lens_radius; dc.type = c.type;
     p.W = rp.width; p.H = rp.height; p.maxDepth = rp.max_depth; p.aaMode = rp.aa_mode;
     p.seedLo = (uint32_t)rp.seed; p.seedHi = (uint32_t)(rp.seed >> 32);
     p.directLighting = rp.direct_lighting ? 1 : 0;
+    p.refill = rp.refill_threshold > 0 ? (rp.refill_threshold > 32 ? 32 : rp.refill_threshold) : 24;
     return BRT_OK;
 }
 

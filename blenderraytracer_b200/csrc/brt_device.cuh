@@ -32,6 +32,8 @@ struct DevScene {
     const float4* nodes; // 4 x float4 per BVH node (see bvh.cu)
     const float4* lights;// 2 per light: (v.xyz, type), (color*intensity .xyz, 0)
     const unsigned char* perm;  // 512-entry doubled Perlin permutation      noise.js:7-17
+    const double* prim64; // 9 doubles per primitive (unified index, as meta): float64 copy used ONLY to evaluate the
+                          // primitive a PRIMARY ray's fp32 traversal selected (t / P / N within 1e-5 of the float64 reference)
     int nSph, nPln, nBox, nTri;
     int baseSph, basePln, baseBox, baseTri;   // offsets into meta
     int nNodes, nLights;
@@ -40,15 +42,12 @@ struct DevScene {
     int bvhStackDepth;
 };
 
-struct DevCamera {         // camera.js:14-35 (derived on the host in float64, rounded once to fp32)
-    float ox, oy, oz;
-    float llx, lly, llz;
-    float hx, hy, hz;
-    float vx, vy, vz;
-    float ux, uy, uz;      // camera.u
-    float wx, wy, wz;      // camera.w
-    float vvx, vvy, vvz;   // camera.v
-    float lensRadius;
+struct DevCamera {         // camera.js:14-35, derived on the host, kept in float64: primary rays are generated in double
+    double o[3];           // (12 DFMA per camera sample) and rounded once to fp32 for traversal
+    double ll[3];          // lowerLeftCorner
+    double h[3], v[3];     // horizontal, vertical
+    double cu[3], cv[3], cw[3];   // camera.u / .v / .w
+    double lensRadius;
     int type;
 };
 
@@ -57,25 +56,31 @@ struct Counters {          // counting build
 };
 
 // ------------------------------------------------------------------------------------------- float3 helpers
+// Every operation is spelled with an explicit rounding intrinsic (or an explicit fmaf), so nvcc's context-dependent
+// mul+add contraction cannot make the same expression round differently in two instantiations: the brute-force and BVH
+// kernels then produce bit-identical hits, hit points and scattered rays (tests: BVH must not change results).
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
-__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z)); }
 __device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
-__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, __fmul_rn(a.x, b.x))); }
 __device__ __forceinline__ float3 cross(float3 a, float3 b) {
-    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return f3(fmaf(a.y, b.z, -__fmul_rn(a.z, b.y)), fmaf(a.z, b.x, -__fmul_rn(a.x, b.z)), fmaf(a.x, b.y, -__fmul_rn(a.y, b.x)));
 }
+__device__ __forceinline__ float3 madd(float3 a, float s, float3 b) { return f3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }   // a*s + b
 __device__ __forceinline__ float3 normalize0(float3 a) {                  // math.js:18 (zero vector stays zero)
     float l2 = dot(a, a);
     return l2 > 0.f ? a * rsqrtf(l2) : f3(0.f, 0.f, 0.f);
 }
 __device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
-__device__ __forceinline__ float3 reflect(float3 v, float3 n) { return v - n * (2.f * dot(v, n)); }   // math.js:19
+__device__ __forceinline__ float3 reflect(float3 v, float3 n) { return madd(n, -2.f * dot(v, n), v); }   // math.js:19
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }   // FMNMX3 (sm_100)
+__device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
 // ------------------------------------------------------------------------------------------- Philox4x32-10
 // Stands in for Math.random (math.js:21-31).  counter = (pixel, sample, block, tag), key = seed.
@@ -116,18 +121,19 @@ struct RngSeq {
 // rejected by the reference); in fp32 it is noise of either sign, so that root is dropped analytically.
 
 // geometry.js:15-29.  Discriminant evaluated as a*(r^2 - |oc - (hb/a) D|^2) (cancellation-robust form of hb^2 - a c).
-__device__ __forceinline__ bool hit_sphere(float4 s, float3 O, float3 D, float a, float inva, float tMin, bool self, float& t) {
-    float3 oc = f3(O.x - s.x, O.y - s.y, O.z - s.z);
+__device__ __forceinline__ bool hit_sphere(float4 s, float3 O, float3 D, float tMin, bool self, float& t) {
+    float a = dot(D, D), inva = __frcp_rn(a);
+    float3 oc = O - f3(s.x, s.y, s.z);
     float hb = dot(oc, D);
-    if (self) { t = -2.f * hb * inva; return t >= tMin; }
-    float k = hb * inva;
-    float3 l = f3(oc.x - k * D.x, oc.y - k * D.y, oc.z - k * D.z);
-    float disc = s.w * s.w - dot(l, l);
+    if (self) { t = __fmul_rn(__fmul_rn(-2.f, hb), inva); return t >= tMin; }
+    float k = __fmul_rn(hb, inva);
+    float3 l = madd(D, -k, oc);
+    float disc = fmaf(s.w, s.w, -dot(l, l));
     if (disc < 0.f) return false;
-    float sq = sqrtf(a * disc);
-    float root = (-hb - sq) * inva;
+    float sq = sqrtf(__fmul_rn(a, disc));
+    float root = __fmul_rn(-hb - sq, inva);
     if (root < tMin) {
-        root = (-hb + sq) * inva;
+        root = __fmul_rn(sq - hb, inva);
         if (!(root >= tMin)) return false;
     }
     t = root;
@@ -135,26 +141,28 @@ __device__ __forceinline__ bool hit_sphere(float4 s, float3 O, float3 D, float a
 }
 // geometry.js:56-61
 __device__ __forceinline__ bool hit_plane(float4 n, float4 p, float3 O, float3 D, float tMin, float& t) {
-    float denom = n.x * D.x + n.y * D.y + n.z * D.z;
+    float3 N = xyz(n);
+    float denom = dot(N, D);
     if (fabsf(denom) < 1e-6f) return false;
-    float tt = ((p.x - O.x) * n.x + (p.y - O.y) * n.y + (p.z - O.z) * n.z) / denom;
+    float tt = __fdiv_rn(dot(xyz(p) - O, N), denom);
     if (!(tt >= tMin)) return false;
     t = tt;
     return true;
 }
 // geometry.js:85-112.  `face` returns 0..5 = x-,x+,y-,y+,z-,z+ : the slab plane that produced t (the reference picks
 // the face by |p - face| < 1e-6, :119-126, which is the same face away from edges; ties resolve x, y, z as there).
-__device__ __forceinline__ bool hit_box(float4 mn, float4 mx, float3 O, float3 D, float3 inv, float tMin, bool self, float& t, int& face) {
-    float t0 = (mn.x - O.x) * inv.x, t1 = (mx.x - O.x) * inv.x;
+__device__ __forceinline__ bool hit_box(float4 mn, float4 mx, float3 O, float3 D, float tMin, bool self, float& t, int& face) {
+    float3 inv = f3(__frcp_rn(D.x), __frcp_rn(D.y), __frcp_rn(D.z));
+    float t0 = __fmul_rn(mn.x - O.x, inv.x), t1 = __fmul_rn(mx.x - O.x, inv.x);
     int fe = 0, fx = 1;                         // entering / exiting face ids
     if (t0 > t1) { float tmp = t0; t0 = t1; t1 = tmp; fe = 1; fx = 0; }
-    float y0 = (mn.y - O.y) * inv.y, y1 = (mx.y - O.y) * inv.y;
+    float y0 = __fmul_rn(mn.y - O.y, inv.y), y1 = __fmul_rn(mx.y - O.y, inv.y);
     int fye = 2, fyx = 3;
     if (y0 > y1) { float tmp = y0; y0 = y1; y1 = tmp; fye = 3; fyx = 2; }
     if (t0 > y1 || y0 > t1) return false;
     if (y0 > t0) { t0 = y0; fe = fye; }         // Math.max(tMinBox, tMinY): x wins ties
     if (y1 < t1) { t1 = y1; fx = fyx; }
-    float z0 = (mn.z - O.z) * inv.z, z1 = (mx.z - O.z) * inv.z;
+    float z0 = __fmul_rn(mn.z - O.z, inv.z), z1 = __fmul_rn(mx.z - O.z, inv.z);
     int fze = 4, fzx = 5;
     if (z0 > z1) { float tmp = z0; z0 = z1; z1 = tmp; fze = 5; fzx = 4; }
     if (t0 > z1 || z0 > t1) return false;
@@ -179,16 +187,16 @@ __device__ __forceinline__ bool hit_tri(float4 v0, float4 e1, float4 e2, float3 
     float3 h = cross(D, E2);
     float a = dot(E1, h);
     if (fabsf(a) < 0.0001f) return false;
-    float f = 1.0f / a;
-    float3 s = f3(O.x - v0.x, O.y - v0.y, O.z - v0.z);
-    float u = f * dot(s, h);
+    float f = __frcp_rn(a);
+    float3 s = O - xyz(v0);
+    float u = __fmul_rn(f, dot(s, h));
     if (u < 0.f || u > 1.f) return false;
     if (COUNT) cnt.triB++;
     float3 q = cross(s, E1);
-    float v = f * dot(D, q);
-    if (v < 0.f || u + v > 1.f) return false;
+    float v = __fmul_rn(f, dot(D, q));
+    if (v < 0.f || __fadd_rn(u, v) > 1.f) return false;
     if (COUNT) cnt.triC++;
-    float tt = f * dot(E2, q);
+    float tt = __fmul_rn(f, dot(E2, q));
     if (!(tt >= tMin)) return false;
     t = tt;
     return true;
@@ -197,7 +205,6 @@ __device__ __forceinline__ bool hit_tri(float4 v0, float4 e1, float4 e2, float3 
 struct Hit {
     float t;
     uint32_t pid;
-    int face;      // box face id when pid is a box
 };
 
 // Tie rule: across objects the FIRST object wins an exact tie (world.js:26 `hit.t < closestT`);
@@ -214,23 +221,22 @@ static __device__ __noinline__ bool tie_wins(const DevScene& sc, uint32_t cand, 
     return mc.z > mb.z;
 }
 template <bool SHADOW>
-__device__ __forceinline__ void consider(const DevScene& sc, Hit& best, float t, uint32_t pid, int face) {
+__device__ __forceinline__ void consider(const DevScene& sc, Hit& best, float t, uint32_t pid) {
     if (SHADOW) {
         // any-hit for the direct-lighting extension: strictly closer than the light, emissive primitives ignored
         if (t < best.t) {
             int4 m = __ldg(&sc.meta[meta_index(sc, pid)]);
-            if (__ldg(&sc.matType[m.y]) != 3) { best.t = t; best.pid = pid; best.face = face; }
+            if (__ldg(&sc.matType[m.y]) != 3) { best.t = t; best.pid = pid; }
         }
         return;
     }
     if (t < best.t || (t == best.t && best.pid != PID_NONE && tie_wins(sc, pid, best.pid))) {
-        best.t = t; best.pid = pid; best.face = face;
+        best.t = t; best.pid = pid;
     }
 }
 
 template <bool COUNT, bool SHADOW>
-__device__ __forceinline__ void test_prim(const DevScene& sc, uint32_t pid, float3 O, float3 D, float3 inv, float a, float inva,
-                                          float tMin, uint32_t self, Hit& best, Counters& cnt) {
+__device__ __forceinline__ void test_prim(const DevScene& sc, uint32_t pid, float3 O, float3 D, float tMin, uint32_t self, Hit& best, Counters& cnt) {
     uint32_t ty = pid_type(pid), ix = pid_index(pid);
     float t; int face = 0;
     bool h;
@@ -240,12 +246,12 @@ __device__ __forceinline__ void test_prim(const DevScene& sc, uint32_t pid, floa
         h = hit_tri<COUNT>(ldg4(sc.tri + 3 * ix), ldg4(sc.tri + 3 * ix + 1), ldg4(sc.tri + 3 * ix + 2), O, D, tMin, t, cnt);
     } else if (ty == PT_SPHERE) {
         if (COUNT) cnt.sph++;
-        h = hit_sphere(ldg4(sc.sph + ix), O, D, a, inva, tMin, pid == self, t);
+        h = hit_sphere(ldg4(sc.sph + ix), O, D, tMin, pid == self, t);
     } else {
         if (COUNT) cnt.box++;
-        h = hit_box(ldg4(sc.box + 2 * ix), ldg4(sc.box + 2 * ix + 1), O, D, inv, tMin, pid == self, t, face);
+        h = hit_box(ldg4(sc.box + 2 * ix), ldg4(sc.box + 2 * ix + 1), O, D, tMin, pid == self, t, face);
     }
-    if (h && t <= best.t) consider<SHADOW>(sc, best, t, pid, face);
+    if (h && t <= best.t) consider<SHADOW>(sc, best, t, pid);
 }
 
 // Unbounded planes live outside the BVH in a linear list (world.js:24-30 order is irrelevant given the tie rule).
@@ -256,7 +262,7 @@ __device__ __forceinline__ void test_planes(const DevScene& sc, float3 O, float3
         if (pid == self) continue;
         if (COUNT) cnt.pln++;
         float t;
-        if (hit_plane(ldg4(sc.pln + 2 * i), ldg4(sc.pln + 2 * i + 1), O, D, tMin, t) && t <= best.t) consider<SHADOW>(sc, best, t, pid, 0);
+        if (hit_plane(ldg4(sc.pln + 2 * i), ldg4(sc.pln + 2 * i + 1), O, D, tMin, t) && t <= best.t) consider<SHADOW>(sc, best, t, pid);
     }
 }
 
@@ -264,13 +270,11 @@ __device__ __forceinline__ void test_planes(const DevScene& sc, float3 O, float3
 // Brute force: the reference's own O(N) loops (world.js:24-30, geometry.js:253-259) over the SoA arrays.
 template <bool COUNT, bool SHADOW>
 __device__ __forceinline__ Hit trace_brute(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt) {
-    Hit best; best.t = tMax; best.pid = PID_NONE; best.face = 0;
-    float a = dot(D, D), inva = 1.0f / a;
-    float3 inv = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
+    Hit best; best.t = tMax; best.pid = PID_NONE;
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
-    for (int i = 0; i < sc.nSph; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_SPHERE, i), O, D, inv, a, inva, tMin, self, best, cnt);
-    for (int i = 0; i < sc.nBox; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_BOX, i), O, D, inv, a, inva, tMin, self, best, cnt);
-    for (int i = 0; i < sc.nTri; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_TRI, i), O, D, inv, a, inva, tMin, self, best, cnt);
+    for (int i = 0; i < sc.nSph; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_SPHERE, i), O, D, tMin, self, best, cnt);
+    for (int i = 0; i < sc.nBox; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_BOX, i), O, D, tMin, self, best, cnt);
+    for (int i = 0; i < sc.nTri; i++) test_prim<COUNT, SHADOW>(sc, make_pid(PT_TRI, i), O, D, tMin, self, best, cnt);
     return best;
 }
 
@@ -282,51 +286,69 @@ __device__ __forceinline__ Hit trace_brute(const DevScene& sc, float3 O, float3 
 // free); deeper entries (rare) spill to a per-thread local array.
 constexpr int SMEM_STACK = 20;
 constexpr int LOCAL_STACK = 44;
+constexpr uint32_t TRAV_DONE = 0xFFFFFFFFu;
 
+struct RayInv { float3 inv, ood; };
+__device__ __forceinline__ RayInv ray_inv(float3 O, float3 D) {
+    RayInv r;
+    r.inv = f3(__frcp_rn(D.x), __frcp_rn(D.y), __frcp_rn(D.z));
+    r.ood = O * r.inv;
+    return r;
+}
+
+// One internal-node visit: slab-tests both children against [0, tBest] and returns the next node to visit (TRAV_DONE-free:
+// `hitAny` false = neither child is hit); `farc` is valid when both were hit.  12 FFMA + 12 FMNMX + 4 FMNMX3.
+__device__ __forceinline__ bool node_visit(const float4* __restrict__ nodes, uint32_t cur, const RayInv& r, float tBest,
+                                           uint32_t& nearc, uint32_t& farc, bool& both) {
+    const float4* np = nodes + 4 * (size_t)cur;
+    float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
+    float4 n3f = ldg4(np + 3);
+    uint32_t c0 = __float_as_uint(n3f.x), c1 = __float_as_uint(n3f.y);
+    float ax0 = fmaf(n0.x, r.inv.x, -r.ood.x), ax1 = fmaf(n0.y, r.inv.x, -r.ood.x);
+    float ay0 = fmaf(n0.z, r.inv.y, -r.ood.y), ay1 = fmaf(n0.w, r.inv.y, -r.ood.y);
+    float az0 = fmaf(n2.x, r.inv.z, -r.ood.z), az1 = fmaf(n2.y, r.inv.z, -r.ood.z);
+    float bx0 = fmaf(n1.x, r.inv.x, -r.ood.x), bx1 = fmaf(n1.y, r.inv.x, -r.ood.x);
+    float by0 = fmaf(n1.z, r.inv.y, -r.ood.y), by1 = fmaf(n1.w, r.inv.y, -r.ood.y);
+    float bz0 = fmaf(n2.z, r.inv.z, -r.ood.z), bz1 = fmaf(n2.w, r.inv.z, -r.ood.z);
+    float tn0 = fmaxf(fmax3(fminf(ax0, ax1), fminf(ay0, ay1), fminf(az0, az1)), 0.f);
+    float tf0 = fminf(fmin3(fmaxf(ax0, ax1), fmaxf(ay0, ay1), fmaxf(az0, az1)), tBest);
+    float tn1 = fmaxf(fmax3(fminf(bx0, bx1), fminf(by0, by1), fminf(bz0, bz1)), 0.f);
+    float tf1 = fminf(fmin3(fmaxf(bx0, bx1), fmaxf(by0, by1), fmaxf(bz0, bz1)), tBest);
+    // conservative: boxes are inflated at build time and the far bound is widened by a few ulps (the slab arithmetic's
+    // own error grows with the distance to the ray origin), so the BVH can only add candidates, never lose one the
+    // brute-force loop would have found.
+    bool h0 = tn0 <= __fmul_rn(tf0, 1.0000005f), h1 = tn1 <= __fmul_rn(tf1, 1.0000005f);
+    bool swap = tn1 < tn0;
+    both = h0 & h1;
+    nearc = both ? (swap ? c1 : c0) : (h0 ? c0 : c1);
+    farc = swap ? c0 : c1;
+    return h0 | h1;
+}
+
+// Blocking traversal (primary AOVs, shadow rays): runs one ray to completion.
 template <bool COUNT, bool SHADOW>
 __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
                                          uint32_t* sstack /* &smem[threadIdx.x] */, int sstride) {
-    Hit best; best.t = tMax; best.pid = PID_NONE; best.face = 0;
-    float a = dot(D, D), inva = 1.0f / a;
-    float3 inv = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
+    Hit best; best.t = tMax; best.pid = PID_NONE;
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
     if (sc.nNodes == 0) return best;
-    float3 ood = f3(O.x * inv.x, O.y * inv.y, O.z * inv.z);
+    RayInv r = ray_inv(O, D);
     uint32_t lstack[LOCAL_STACK];
     int sp = 0;
     uint32_t cur = 0;
-    const float4* __restrict__ nodes = sc.nodes;
     for (;;) {
         if (cur & LEAF_BIT) {
-            test_prim<COUNT, SHADOW>(sc, cur & ~LEAF_BIT, O, D, inv, a, inva, tMin, self, best, cnt);
+            test_prim<COUNT, SHADOW>(sc, cur & ~LEAF_BIT, O, D, tMin, self, best, cnt);
             if (SHADOW && best.pid != PID_NONE) break;
         } else {
-            const float4* np = nodes + 4 * (size_t)cur;
-            float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
-            float4 n3f = ldg4(np + 3);
-            uint32_t c0 = __float_as_uint(n3f.x), c1 = __float_as_uint(n3f.y);
             if (COUNT) cnt.aabb += 2;
-            float ax0 = fmaf(n0.x, inv.x, -ood.x), ax1 = fmaf(n0.y, inv.x, -ood.x);
-            float ay0 = fmaf(n0.z, inv.y, -ood.y), ay1 = fmaf(n0.w, inv.y, -ood.y);
-            float az0 = fmaf(n2.x, inv.z, -ood.z), az1 = fmaf(n2.y, inv.z, -ood.z);
-            float bx0 = fmaf(n1.x, inv.x, -ood.x), bx1 = fmaf(n1.y, inv.x, -ood.x);
-            float by0 = fmaf(n1.z, inv.y, -ood.y), by1 = fmaf(n1.w, inv.y, -ood.y);
-            float bz0 = fmaf(n2.z, inv.z, -ood.z), bz1 = fmaf(n2.w, inv.z, -ood.z);
-            float tn0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.f));
-            float tf0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best.t));
-            float tn1 = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.f));
-            float tf1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), best.t));
-            // conservative: boxes are inflated at build time and the far bound is widened by a few ulps, so the BVH can
-            // only add candidates, never lose one the brute-force loop would have found.
-            bool h0 = tn0 <= tf0 * 1.0000005f, h1 = tn1 <= tf1 * 1.0000005f;
-            if (h0 | h1) {
-                if (h0 & h1) {
-                    bool swap = tn1 < tn0;
-                    uint32_t nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+            uint32_t nearc, farc; bool both;
+            if (node_visit(sc.nodes, cur, r, best.t, nearc, farc, both)) {
+                if (both) {
                     if (sp < SMEM_STACK) sstack[sp * sstride] = farc; else lstack[sp - SMEM_STACK] = farc;
                     sp++;
-                    cur = nearc;
-                } else cur = h0 ? c0 : c1;
+                }
+                cur = nearc;
                 continue;
             }
         }
@@ -337,27 +359,109 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
     return best;
 }
 
-// ------------------------------------------------------------------------------------------- surface frame
+// ------------------------------------------------------------------------------------------- float64 primary hits
+// Mixed precision by design: fp32 traversal SELECTS the primitive; for primary rays the selected primitive is then
+// re-evaluated in float64 from the float64 camera ray (one primitive, ~60 DFMA per camera sample), which puts t, P and N
+// within rounding of the float64 reference even at silhouettes and grazing angles where fp32 is ill-conditioned.
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ D3 normalize0(D3 a) { double l = sqrt(dot(a, a)); return l > 0 ? a * (1.0 / l) : d3(0, 0, 0); }
+__device__ __forceinline__ D3 ldd3(const double* p) { return d3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+__device__ __forceinline__ float3 tof3(D3 a) { return f3((float)a.x, (float)a.y, (float)a.z); }
+
 struct Surface {
     float3 P, N;        // hit point, shading normal after setFaceNormal (math.js:55-58)
     bool front;
     int objId, matId, triId;
 };
-__device__ __forceinline__ Surface make_surface(const DevScene& sc, const Hit& h, float3 O, float3 D) {
+
+// Returns false when the float64 evaluation rejects the primitive fp32 selected (a silhouette flip): the caller keeps fp32.
+static __device__ __noinline__ bool refine_primary(const DevScene& sc, uint32_t pid, D3 O, D3 D, double& tOut, Surface& s) {
+    const uint32_t ty = pid_type(pid);
+    const double* q = sc.prim64 + 9 * (size_t)meta_index(sc, pid);
+    const double tMin = 0.001;
+    double t; D3 n;
+    if (ty == PT_SPHERE) {                                                     // geometry.js:15-34
+        D3 c = ldd3(q); double r = __ldg(q + 3);
+        D3 oc = O - c;
+        double a = dot(D, D), hb = dot(oc, D), cc = dot(oc, oc) - r * r;
+        double disc = hb * hb - a * cc;
+        if (disc < 0) return false;
+        double sq = sqrt(disc);
+        t = (-hb - sq) / a;
+        if (t < tMin) { t = (-hb + sq) / a; if (!(t >= tMin)) return false; }
+        D3 P = O + D * t;
+        n = (P - c) * (1.0 / r);
+    } else if (ty == PT_PLANE) {                                               // geometry.js:56-61
+        n = ldd3(q);
+        double den = dot(n, D);
+        if (fabs(den) < 1e-6) return false;
+        t = dot(ldd3(q + 3) - O, n) / den;
+        if (!(t >= tMin)) return false;
+    } else if (ty == PT_BOX) {                                                 // geometry.js:85-126 incl. the |p - face| < 1e-6 face rule
+        D3 mn = ldd3(q), mx = ldd3(q + 3);
+        double t0 = (mn.x - O.x) / D.x, t1 = (mx.x - O.x) / D.x;
+        if (t0 > t1) { double w = t0; t0 = t1; t1 = w; }
+        double y0 = (mn.y - O.y) / D.y, y1 = (mx.y - O.y) / D.y;
+        if (y0 > y1) { double w = y0; y0 = y1; y1 = w; }
+        if (t0 > y1 || y0 > t1) return false;
+        t0 = fmax(t0, y0); t1 = fmin(t1, y1);
+        double z0 = (mn.z - O.z) / D.z, z1 = (mx.z - O.z) / D.z;
+        if (z0 > z1) { double w = z0; z0 = z1; z1 = w; }
+        if (t0 > z1 || z0 > t1) return false;
+        t0 = fmax(t0, z0); t1 = fmin(t1, z1);
+        t = t0 > tMin ? t0 : t1;
+        if (!(t >= tMin)) return false;
+        D3 P = O + D * t;
+        const double eps = 1e-6;
+        if (fabs(P.x - mn.x) < eps) n = d3(-1, 0, 0);
+        else if (fabs(P.x - mx.x) < eps) n = d3(1, 0, 0);
+        else if (fabs(P.y - mn.y) < eps) n = d3(0, -1, 0);
+        else if (fabs(P.y - mx.y) < eps) n = d3(0, 1, 0);
+        else if (fabs(P.z - mn.z) < eps) n = d3(0, 0, -1);
+        else n = d3(0, 0, 1);
+    } else {                                                                   // geometry.js:148-175
+        D3 v0 = ldd3(q), e1 = ldd3(q + 3) - v0, e2 = ldd3(q + 6) - v0;
+        D3 h = cross(D, e2);
+        double a = dot(e1, h);
+        if (fabs(a) < 0.0001) return false;
+        double f = 1.0 / a;
+        D3 sv = O - v0;
+        D3 qq = cross(sv, e1);
+        t = f * dot(e2, qq);
+        if (!(t >= tMin)) return false;
+        n = normalize0(cross(e1, e2));
+    }
+    D3 P = O + D * t;
+    bool front = dot(D, n) < 0;
+    s.P = tof3(P);
+    s.N = front ? tof3(n) : tof3(n * -1.0);
+    s.front = front;
+    tOut = t;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------- surface frame
+__device__ __forceinline__ Surface make_surface(const DevScene& sc, const Hit& h, float3 O, float3 D, uint32_t self) {
     Surface s;
-    s.P = f3(O.x + h.t * D.x, O.y + h.t * D.y, O.z + h.t * D.z);          // Ray.at (math.js:41)
+    s.P = madd(D, h.t, O);                                                     // Ray.at (math.js:41)
     uint32_t ty = pid_type(h.pid), ix = pid_index(h.pid);
     int4 m = __ldg(&sc.meta[meta_index(sc, h.pid)]);
     s.objId = m.x; s.matId = m.y; s.triId = m.z;
     float3 n;
     if (ty == PT_SPHERE) {
         float4 sp = ldg4(sc.sph + ix);
-        float ir = 1.0f / sp.w;                                            // geometry.js:34 (negative radius flips)
-        n = f3((s.P.x - sp.x) * ir, (s.P.y - sp.y) * ir, (s.P.z - sp.z) * ir);
+        n = (s.P - f3(sp.x, sp.y, sp.z)) * __frcp_rn(sp.w);                    // geometry.js:34 (negative radius flips)
     } else if (ty == PT_PLANE) {
         n = xyz(ldg4(sc.pln + 2 * ix));
     } else if (ty == PT_BOX) {
-        int f = h.face;
+        float t; int f = 0;                                                    // the slab plane that produced t (re-derived: keeps `face` out of the traversal state)
+        hit_box(ldg4(sc.box + 2 * ix), ldg4(sc.box + 2 * ix + 1), O, D, 0.001f, h.pid == self, t, f);
         float sgn = (f & 1) ? 1.f : -1.f;
         n = f3((f >> 1) == 0 ? sgn : 0.f, (f >> 1) == 1 ? sgn : 0.f, (f >> 1) == 2 ? sgn : 0.f);
     } else {

@@ -7,6 +7,8 @@
 namespace brt {
 
 constexpr int PT_BLOCK = 128;
+constexpr int PT_MIN_BLOCKS = 6;     // __launch_bounds__ min blocks/SM for the megakernel (<= 80 registers)
+constexpr int PT_COLD_SLOTS = 10;    // shared-memory words of cold per-path state per thread
 
 struct PTParams {
     DevScene sc;
@@ -17,6 +19,8 @@ struct PTParams {
     int aaMode;
     uint32_t seedLo, seedHi;
     int directLighting;
+    int stackSlots;              // shared-memory traversal-stack entries per thread (set by the launcher)
+    int refill;                  // megakernel: go back to shading when fewer than this many lanes of a warp still traverse
     float4* accum;               // W*H fp32 RGBA sums (alpha = number of samples)
     unsigned long long* counters;// 8 x u64 (Counters), counting build only
 };

@@ -59,7 +59,7 @@ class RayTracer:
                                  "(device=-1 gives a host-only context for scene/camera logic, which cannot render)")
         self._ctx = h
         if stream is not None:
-            L.check(self._ctx, self._L.brt_set_stream(self._ctx, C.c_void_p(int(stream))))
+            L.check(self._ctx, self._L.brt_set_stream(self._ctx, C.c_void_p(int(stream) or 1)))
         self.width, self.height = int(width), int(height)
         # ray-tracer.js:23-30
         self.maxBounces = 5
@@ -357,6 +357,7 @@ class RayTracer:
         p.direct_lighting = 1 if self.directLighting else 0
         p.sampler, p.integrator, p.accel = L.SAMPLER[self.sampler], L.INTEGRATOR[self.integrator], L.ACCEL[self.accel]
         p.spp_batch, p.count_tests = int(self.sppBatch), 1 if self.countTests else 0
+        p.refill_threshold = int(getattr(self, "refillThreshold", 0))
         L.check(self._ctx, self._L.brt_set_render_params(self._ctx, C.byref(p)))
         return p
 
@@ -466,7 +467,12 @@ class RayTracer:
 
     # device-resident path (multi-GPU spp split; bench.py)
     def setStream(self, cuda_stream):
-        L.check(self._ctx, self._L.brt_set_stream(self._ctx, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+        """`cuda_stream`: a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream; 0 = the legacy default
+        stream, passed on as cudaStreamLegacy = 0x1), or None to go back to the ctx-owned stream."""
+        if cuda_stream is None:
+            L.check(self._ctx, self._L.brt_set_stream(self._ctx, None))
+        else:
+            L.check(self._ctx, self._L.brt_set_stream(self._ctx, C.c_void_p(int(cuda_stream) or 1)))
 
     def renderAccumulate(self, d_accum_ptr, sample_begin, sample_count):
         L.check(self._ctx, self._L.brt_render_accumulate(self._ctx, C.c_void_p(int(d_accum_ptr)) if d_accum_ptr else None,

@@ -130,6 +130,8 @@ typedef struct brt_render_params {
     int32_t accel;               /* BRT_ACCEL_* */
     int32_t spp_batch;           /* samples per launch between progress callbacks / cancel polls; 0 = auto */
     int32_t count_tests;         /* 1 = counting build of the same traversal (fills brt_stats.tests_*) */
+    int32_t refill_threshold;    /* megakernel tuning: warps return to shading when fewer lanes than this still traverse; 0 = default */
+    int32_t _pad1;
 } brt_render_params;
 
 typedef struct brt_scene_info {
@@ -165,7 +167,8 @@ const char* brt_version(void);
 int brt_create(brt_ctx** out, int device_id);
 void brt_destroy(brt_ctx* ctx);
 const char* brt_last_error(const brt_ctx* ctx);
-/* Launch on this cudaStream_t (e.g. torch's current stream) instead of the ctx-owned one; NULL restores it. */
+/* Launch on this cudaStream_t (e.g. torch's current stream) instead of the ctx-owned one; NULL restores it.
+ * The legacy default stream is named by its CUDA handle cudaStreamLegacy = (cudaStream_t)0x1, not by 0. */
 int brt_set_stream(brt_ctx* ctx, void* cuda_stream);
 
 /* ---- scene ------------------------------------------------------------------------------------------- */

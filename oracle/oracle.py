@@ -613,12 +613,17 @@ class OracleRayTracer:
         rp.sampleBegin = int(getattr(self, "sampleBegin", 0))
         return rp
 
-    def render(self, onProgress=None, rect=None):                      # :166-281
-        """Returns RGBA8 (H, W, 4), row 0 = top.  `rect=(x0, y0, x1, y1)` renders a crop (rest stays 0)."""
+    def render(self, onProgress=None, rect=None, reuse=False):         # :166-281
+        """Returns RGBA8 (H, W, 4), row 0 = top.  `rect=(x0, y0, x1, y1)` renders a crop (rest stays 0).
+        `reuse=True` keeps the output arrays between calls (timing loops: no per-call allocation of full frames)."""
         W, H = self.width, self.height
-        rgba = np.zeros((H, W, 4), np.uint8)
-        fdat = np.zeros((H, W, 4), np.float32)
-        lin = np.zeros((H, W, 4), np.float64)
+        if reuse and getattr(self, "_bufs", None) is not None and self._bufs[0].shape == (H, W, 4):
+            rgba, fdat, lin = self._bufs
+        else:
+            rgba = np.zeros((H, W, 4), np.uint8)
+            fdat = np.zeros((H, W, 4), np.float32)
+            lin = np.zeros((H, W, 4), np.float64)
+            self._bufs = (rgba, fdat, lin) if reuse else None
         rp = self._params()
         x0, y0, x1, y1 = rect if rect else (0, 0, W, H)
         self.rays = self.scene.L.orc_render_rect(self.scene.h, C.byref(rp), x0, y0, x1, y1, self.threads,

@@ -126,7 +126,7 @@ def _tie_scene(seed=7):
     lam = lambda c: dict(type="lambertian", color=c)
     for k in range(40):
         c = rng.uniform(-3, 3, 3).round(3).tolist()
-        r = float(rng.uniform(0.2, 0.7).round(3))
+        r = round(float(rng.uniform(0.2, 0.7)), 3)
         objs.append(dict(type="sphere", center=c, radius=r, material=lam([0.5, 0.5, 0.5])))
         if k % 4 == 0:
             objs.append(dict(type="sphere", center=c, radius=r, material=dict(type="metal", color=[0.9, 0.9, 0.9], roughness=0.1)))   # exact duplicate
