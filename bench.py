@@ -205,6 +205,7 @@ def run_ours(args):
     rt.updateRenderSettings(dict(samples=spp, maxBounces=depth))
     rt.sampler, rt.accel, rt.integrator = args.sampler, args.accel, args.integrator
     rt.refillThreshold = args.refill
+    rt.pathsInFlight = args.inflight
     info = rt.sceneInfo()
     sr = SppSplitRenderer(rt, reduce=args.reduce)
 
@@ -385,7 +386,8 @@ def main():
     ap.add_argument("--integrator", default="auto", choices=["auto", "megakernel", "wavefront"])
     ap.add_argument("--reduce", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--refill", type=int, default=0, help="megakernel refill threshold (lanes); 0 = library default")
+    ap.add_argument("--refill", type=int, default=0, help="extend-phase refill threshold (idle lanes); 0 = library default")
+    ap.add_argument("--inflight", type=int, default=0, help="samples of a pixel in flight per lane (1..4); 0 = library default")
     ap.add_argument("--cpu-seconds", type=float, default=14.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -42,7 +42,7 @@ struct brt_ctx {
     int nBounded = 0;
     brt_scene_info info{};
     // frame buffers
-    DevBuf dAccum, dRgba, dFloat, dFloat2, dLinear, dCounters, dScratch;
+    DevBuf dAccum, dRgba, dFloat, dFloat2, dLinear, dCounters, dScratch, dPlanes;
     // fp64 parity data (lazy)
     DevBuf dObj64, dTris64; bool obj64Dirty = true;
     std::atomic<int> cancel{ 0 };
@@ -106,7 +106,7 @@ void brt_destroy(brt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &ctx->dSph, &ctx->dPln, &ctx->dBox, &ctx->dTri, &ctx->dMeta, &ctx->dMat, &ctx->dMatType, &ctx->dLights, &ctx->dPerm, &ctx->dPrim64,
-                       &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch,
+                       &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch, &ctx->dPlanes,
                        &ctx->dObj64, &ctx->dTris64 };
     for (DevBuf* b : bufs) b->release();
     if (ctx->dNodes) cudaFree(ctx->dNodes);
@@ -370,7 +370,8 @@ int brt_set_render_params(brt_ctx* ctx, const brt_render_params* p) {
     if (!ctx || !p) return BRT_E_INVALID;
     if (p->width < 1 || p->height < 1 || p->width > 65536 || p->height > 65536) return fail(ctx, BRT_E_INVALID, "bad image size");
     if (p->spp < 1) return fail(ctx, BRT_E_INVALID, "spp must be >= 1");
-    if (p->max_depth < 0) return fail(ctx, BRT_E_INVALID, "max_depth must be >= 0");
+    if (p->max_depth < 0 || p->max_depth > 250) return fail(ctx, BRT_E_INVALID, "max_depth must be in [0, 250]");
+    if (p->spp > (1 << 24)) return fail(ctx, BRT_E_INVALID, "spp must be <= 2^24");
     if (p->aa_mode < 0 || p->aa_mode > 3 || p->tonemap < 0 || p->tonemap > 2) return fail(ctx, BRT_E_INVALID, "bad aa_mode / tonemap");
     if (p->sampler < 0 || p->sampler > 1 || p->integrator < 0 || p->integrator > 2 || p->accel < 0 || p->accel > 2)
         return fail(ctx, BRT_E_INVALID, "bad sampler / integrator / accel");
@@ -415,7 +416,9 @@ static int prepare(brt_ctx* ctx, PTParams& p) {
     p.W = rp.width; p.H = rp.height; p.maxDepth = rp.max_depth; p.aaMode = rp.aa_mode;
     p.seedLo = (uint32_t)rp.seed; p.seedHi = (uint32_t)(rp.seed >> 32);
     p.directLighting = rp.direct_lighting ? 1 : 0;
-    p.refill = rp.refill_threshold > 0 ? (rp.refill_threshold > 32 ? 32 : rp.refill_threshold) : 24;
+    p.refill = rp.refill_threshold > 0 ? (rp.refill_threshold > 32 ? 32 : rp.refill_threshold) : 8;
+    p.wavefront = rp.integrator == BRT_INTEGRATOR_WAVEFRONT ? 1 : 0;   // AUTO = megakernel: faster on every measured config
+    p.inflight = (rp.paths_in_flight >= 1 && rp.paths_in_flight <= 4) ? rp.paths_in_flight : 2;
     return BRT_OK;
 }
 
@@ -438,7 +441,21 @@ static int launch_samples(brt_ctx* ctx, PTParams& p, float* dAccum, int sBegin, 
         p.counters = (unsigned long long*)ctx->dCounters.p;
     }
     if (p.maxDepth <= 0) return BRT_OK;                             // rayColor(depth <= 0) is black (ray-tracer.js:103)
-    CK(launch_pathtrace(p, ctx->rp.sampler, use_bvh(ctx), count, z_split(ctx, sCount), ctx->stream));
+    const int z = z_split(ctx, sCount);
+    if (z > 1) {
+        // small image: split the samples over z chunks to fill the GPU; every chunk accumulates into its own zeroed plane
+        // and the planes are folded in fixed order (no atomics: results are bit-reproducible)
+        const size_t px = (size_t)p.W * p.H;
+        CK(ctx->dPlanes.ensure(px * 16 * (size_t)z));
+        CK(cudaMemsetAsync(ctx->dPlanes.p, 0, px * 16 * (size_t)z, ctx->stream));
+        p.accum = (float4*)ctx->dPlanes.p; p.planeStride = px;
+        CK(launch_pathtrace(p, ctx->rp.sampler, use_bvh(ctx), count, z, ctx->stream));
+        CK(launch_sum_planes((float4*)dAccum, (const float4*)ctx->dPlanes.p, z, px, ctx->stream));
+        ctx->stats.launches += 2;
+        return BRT_OK;
+    }
+    p.planeStride = 0;
+    CK(launch_pathtrace(p, ctx->rp.sampler, use_bvh(ctx), count, 1, ctx->stream));
     ctx->stats.launches++;
     return BRT_OK;
 }

@@ -98,18 +98,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 constexpr uint32_t PHILOX_TAG = 0x42525431u;   // "BRT1"
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-// Sequential stream for BRT_SAMPLER_REFERENCE: the reference's draw order, one uniform at a time.
+// Sequential stream for BRT_SAMPLER_REFERENCE: the reference's draw order, one uniform at a time.  The whole state is
+// one counter (`pos` = uniforms consumed so far), so a path can be suspended to shared memory and resumed.
 struct RngSeq {
-    uint32_t pix, samp, blk, k0, k1;
+    uint32_t pix, samp, pos, k0, k1;
     uint4 buf;
-    int have;
-    __device__ __forceinline__ void init(uint32_t pixel, uint32_t sample, uint32_t seedLo, uint32_t seedHi) {
-        pix = pixel; samp = sample; blk = 0; k0 = seedLo; k1 = seedHi; have = 0;
+    __device__ __forceinline__ void init(uint32_t pixel, uint32_t sample, uint32_t seedLo, uint32_t seedHi) { resume(pixel, sample, 0u, seedLo, seedHi); }
+    __device__ __forceinline__ void resume(uint32_t pixel, uint32_t sample, uint32_t position, uint32_t seedLo, uint32_t seedHi) {
+        pix = pixel; samp = sample; pos = position; k0 = seedLo; k1 = seedHi;
+        if (pos & 3u) buf = philox4x32_10(pix, samp, pos >> 2, PHILOX_TAG, k0, k1);
     }
     __device__ __forceinline__ float next() {
-        if (have == 0) { buf = philox4x32_10(pix, samp, blk, PHILOX_TAG, k0, k1); blk++; have = 4; }
-        uint32_t v = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
-        have--;
+        uint32_t k = pos & 3u;
+        if (k == 0u) buf = philox4x32_10(pix, samp, pos >> 2, PHILOX_TAG, k0, k1);
+        uint32_t v = k == 0u ? buf.x : k == 1u ? buf.y : k == 2u ? buf.z : buf.w;
+        pos++;
         return u01(v);
     }
 };
@@ -284,8 +287,8 @@ __device__ __forceinline__ Hit trace_brute(const DevScene& sc, float3 O, float3 
 //   a child with LEAF_BIT set is a primitive id, otherwise an internal node index.
 // Traversal stack: the first SMEM_STACK entries of every thread live in shared memory ([depth][thread], conflict
 // free); deeper entries (rare) spill to a per-thread local array.
-constexpr int SMEM_STACK = 20;
-constexpr int LOCAL_STACK = 44;
+constexpr int SMEM_STACK = 12;
+constexpr int LOCAL_STACK = 52;
 constexpr uint32_t TRAV_DONE = 0xFFFFFFFFu;
 
 struct RayInv { float3 inv, ood; };
@@ -364,13 +367,19 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
 // re-evaluated in float64 from the float64 camera ray (one primitive, ~60 DFMA per camera sample), which puts t, P and N
 // within rounding of the float64 reference even at silhouettes and grazing angles where fp32 is ill-conditioned.
 struct D3 { double x, y, z; };
+// Explicitly rounded, never contracted, in the reference's operation order (math.js:11-19): given the same inputs these
+// produce the same bits as JavaScript, so a primary hit's t equals the float64 reference's t.
 __device__ __forceinline__ D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ D3 cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-__device__ __forceinline__ D3 normalize0(D3 a) { double l = sqrt(dot(a, a)); return l > 0 ? a * (1.0 / l) : d3(0, 0, 0); }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y), __dadd_rn(a.z, b.z)); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y), __dsub_rn(a.z, b.z)); }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(__dmul_rn(a.x, s), __dmul_rn(a.y, s), __dmul_rn(a.z, s)); }
+__device__ __forceinline__ D3 operator/(D3 a, double s) { return d3(__ddiv_rn(a.x, s), __ddiv_rn(a.y, s), __ddiv_rn(a.z, s)); }
+__device__ __forceinline__ double dot(D3 a, D3 b) { return __dadd_rn(__dadd_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dmul_rn(a.z, b.z)); }
+__device__ __forceinline__ D3 cross(D3 a, D3 b) {
+    return d3(__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)), __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
+              __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ D3 normalize0(D3 a) { double l = sqrt(dot(a, a)); return l > 0 ? a / l : d3(0, 0, 0); }
 __device__ __forceinline__ D3 ldd3(const double* p) { return d3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 __device__ __forceinline__ float3 tof3(D3 a) { return f3((float)a.x, (float)a.y, (float)a.z); }
 
@@ -389,29 +398,29 @@ static __device__ __noinline__ bool refine_primary(const DevScene& sc, uint32_t 
     if (ty == PT_SPHERE) {                                                     // geometry.js:15-34
         D3 c = ldd3(q); double r = __ldg(q + 3);
         D3 oc = O - c;
-        double a = dot(D, D), hb = dot(oc, D), cc = dot(oc, oc) - r * r;
-        double disc = hb * hb - a * cc;
+        double a = dot(D, D), hb = dot(oc, D), cc = __dsub_rn(dot(oc, oc), __dmul_rn(r, r));
+        double disc = __dsub_rn(__dmul_rn(hb, hb), __dmul_rn(a, cc));
         if (disc < 0) return false;
         double sq = sqrt(disc);
-        t = (-hb - sq) / a;
-        if (t < tMin) { t = (-hb + sq) / a; if (!(t >= tMin)) return false; }
+        t = __ddiv_rn(__dsub_rn(-hb, sq), a);
+        if (t < tMin) { t = __ddiv_rn(__dadd_rn(-hb, sq), a); if (!(t >= tMin)) return false; }
         D3 P = O + D * t;
-        n = (P - c) * (1.0 / r);
+        n = (P - c) / r;
     } else if (ty == PT_PLANE) {                                               // geometry.js:56-61
         n = ldd3(q);
         double den = dot(n, D);
         if (fabs(den) < 1e-6) return false;
-        t = dot(ldd3(q + 3) - O, n) / den;
+        t = __ddiv_rn(dot(ldd3(q + 3) - O, n), den);
         if (!(t >= tMin)) return false;
     } else if (ty == PT_BOX) {                                                 // geometry.js:85-126 incl. the |p - face| < 1e-6 face rule
         D3 mn = ldd3(q), mx = ldd3(q + 3);
-        double t0 = (mn.x - O.x) / D.x, t1 = (mx.x - O.x) / D.x;
+        double t0 = __ddiv_rn(__dsub_rn(mn.x, O.x), D.x), t1 = __ddiv_rn(__dsub_rn(mx.x, O.x), D.x);
         if (t0 > t1) { double w = t0; t0 = t1; t1 = w; }
-        double y0 = (mn.y - O.y) / D.y, y1 = (mx.y - O.y) / D.y;
+        double y0 = __ddiv_rn(__dsub_rn(mn.y, O.y), D.y), y1 = __ddiv_rn(__dsub_rn(mx.y, O.y), D.y);
         if (y0 > y1) { double w = y0; y0 = y1; y1 = w; }
         if (t0 > y1 || y0 > t1) return false;
         t0 = fmax(t0, y0); t1 = fmin(t1, y1);
-        double z0 = (mn.z - O.z) / D.z, z1 = (mx.z - O.z) / D.z;
+        double z0 = __ddiv_rn(__dsub_rn(mn.z, O.z), D.z), z1 = __ddiv_rn(__dsub_rn(mx.z, O.z), D.z);
         if (z0 > z1) { double w = z0; z0 = z1; z1 = w; }
         if (t0 > z1 || z0 > t1) return false;
         t0 = fmax(t0, z0); t1 = fmin(t1, z1);
@@ -430,17 +439,17 @@ static __device__ __noinline__ bool refine_primary(const DevScene& sc, uint32_t 
         D3 h = cross(D, e2);
         double a = dot(e1, h);
         if (fabs(a) < 0.0001) return false;
-        double f = 1.0 / a;
+        double f = __ddiv_rn(1.0, a);
         D3 sv = O - v0;
         D3 qq = cross(sv, e1);
-        t = f * dot(e2, qq);
+        t = __dmul_rn(f, dot(e2, qq));
         if (!(t >= tMin)) return false;
         n = normalize0(cross(e1, e2));
     }
     D3 P = O + D * t;
     bool front = dot(D, n) < 0;
     s.P = tof3(P);
-    s.N = front ? tof3(n) : tof3(n * -1.0);
+    s.N = front ? tof3(n) : tof3(d3(-n.x, -n.y, -n.z));
     s.front = front;
     tOut = t;
     return true;
@@ -473,18 +482,19 @@ __device__ __forceinline__ Surface make_surface(const DevScene& sc, const Hit& h
 }
 
 // ------------------------------------------------------------------------------------------- backgrounds (world.js:35-110)
-__device__ __forceinline__ float perlin_fade(float t) { return t * t * t * (t * (t * 6.f - 15.f) + 10.f); }      // noise.js:20
+// (explicit fmaf / __fmul_rn throughout: see the note on pinned numerics at the top of this file)
+__device__ __forceinline__ float perlin_fade(float t) { return __fmul_rn(__fmul_rn(__fmul_rn(t, t), t), fmaf(t, fmaf(t, 6.f, -15.f), 10.f)); }      // noise.js:20
 __device__ __forceinline__ float perlin_grad(int hash, float x, float y, float z) {                               // noise.js:22-27
     int h = hash & 15;
     float u = h < 8 ? x : y;
     float v = h < 4 ? y : (h == 12 || h == 14) ? x : z;
-    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+    return __fadd_rn((h & 1) == 0 ? u : -u, (h & 2) == 0 ? v : -v);
 }
-__device__ __forceinline__ float lerpf(float t, float a, float b) { return a + t * (b - a); }                       // noise.js:21
+__device__ __forceinline__ float lerpf(float t, float a, float b) { return fmaf(t, __fsub_rn(b, a), a); }          // noise.js:21
 __device__ inline float perlin_noise(const unsigned char* __restrict__ p, float x, float y, float z) {             // noise.js:29-61
     float flx = floorf(x), fly = floorf(y), flz = floorf(z);
     int X = ((int)flx) & 255, Y = ((int)fly) & 255, Z = ((int)flz) & 255;
-    float fx = x - flx, fy = y - fly, fz = z - flz;
+    float fx = __fsub_rn(x, flx), fy = __fsub_rn(y, fly), fz = __fsub_rn(z, flz);
     float u = perlin_fade(fx), v = perlin_fade(fy), w = perlin_fade(fz);
     int A = p[X] + Y, AA = p[A] + Z, AB = p[A + 1] + Z;
     int B = p[X + 1] + Y, BA = p[B] + Z, BB = p[B + 1] + Z;
@@ -494,46 +504,51 @@ __device__ inline float perlin_noise(const unsigned char* __restrict__ p, float 
         lerpf(v, lerpf(u, perlin_grad(p[AA + 1], fx, fy, fz - 1), perlin_grad(p[BA + 1], fx - 1, fy, fz - 1)),
                  lerpf(u, perlin_grad(p[AB + 1], fx, fy - 1, fz - 1), perlin_grad(p[BB + 1], fx - 1, fy - 1, fz - 1))));
 }
+// a*x + b*y + c*z + d*w + e*v with explicit fused steps
+__device__ __forceinline__ float mix5(float a, float x, float b, float y, float c, float z, float d, float w, float e, float v) {
+    return fmaf(e, v, fmaf(d, w, fmaf(c, z, fmaf(b, y, __fmul_rn(a, x)))));
+}
 __device__ inline float3 background(const DevScene& sc, float3 D) {
     float3 dir = normalize0(D);
     float I = sc.skyIntensity;
     switch (sc.bgKind) {
     case 1:                                                                                                         // world.js:42-44
-        return f3(sc.bgR * I, sc.bgG * I, sc.bgB * I);
+        return f3(__fmul_rn(sc.bgR, I), __fmul_rn(sc.bgG, I), __fmul_rn(sc.bgB, I));
     case 2: {                                                                                                       // world.js:74-110
         const float il = 1.1952286093343936f;        // 1/|(-0.3,0.6,-0.5)|
-        float sunDot = fmaxf(0.f, (dir.x * -0.3f + dir.y * 0.6f + dir.z * -0.5f) * il);
+        float sunDot = fmaxf(0.f, __fmul_rn(fmaf(dir.z, -0.5f, fmaf(dir.y, 0.6f, __fmul_rn(dir.x, -0.3f))), il));
         float sunMask = sunDot > 0.96f ? 20.f : 0.f;
-        float corona = fmaxf(0.f, (sunDot - 0.8f) / 0.2f);
-        float c3 = corona * corona * 3.f;
+        float corona = fmaxf(0.f, __fmul_rn(__fsub_rn(sunDot, 0.8f), 5.f));
+        float c3 = __fmul_rn(__fmul_rn(corona, corona), 3.f);
         float y = dir.y;
-        float sky = fmaxf(0.f, y * 0.5f + 0.5f) * 2.f;
-        float ground = fmaxf(0.f, -y * 0.3f);
-        float sc1 = fmaxf(0.f, 1.f - fabsf(y));
-        float scat = sc1 * sc1 * 0.3f;
-        return f3((0.3f * sky + 0.2f * ground + 0.8f * scat + 1.0f * sunMask + 1.0f * c3) * I,
-                  (0.5f * sky + 0.15f * ground + 0.9f * scat + 0.95f * sunMask + 0.8f * c3) * I,
-                  (0.8f * sky + 0.1f * ground + 1.0f * scat + 0.8f * sunMask + 0.6f * c3) * I);
+        float sky = __fmul_rn(fmaxf(0.f, fmaf(y, 0.5f, 0.5f)), 2.f);
+        float ground = fmaxf(0.f, __fmul_rn(y, -0.3f));
+        float sc1 = fmaxf(0.f, __fsub_rn(1.f, fabsf(y)));
+        float scat = __fmul_rn(__fmul_rn(sc1, sc1), 0.3f);
+        return f3(__fmul_rn(mix5(0.3f, sky, 0.2f, ground, 0.8f, scat, 1.0f, sunMask, 1.0f, c3), I),
+                  __fmul_rn(mix5(0.5f, sky, 0.15f, ground, 0.9f, scat, 0.95f, sunMask, 0.8f, c3), I),
+                  __fmul_rn(mix5(0.8f, sky, 0.1f, ground, 1.0f, scat, 0.8f, sunMask, 0.6f, c3), I));
     }
     case 3: {                                                                                                       // world.js:46-72
         const float il = 0.95782628522115137f;       // 1/|(0.3,0.6,0.8)|
-        float sunDot = fmaxf(0.f, (dir.x * 0.3f + dir.y * 0.6f + dir.z * 0.8f) * il);
+        float sunDot = fmaxf(0.f, __fmul_rn(fmaf(dir.z, 0.8f, fmaf(dir.y, 0.6f, __fmul_rn(dir.x, 0.3f))), il));
         float s = sunDot;                             // pow(x, 512) by nine exact squarings
 #pragma unroll
-        for (int k = 0; k < 9; k++) s = s * s;
-        float sun = s * 10.f;
-        float hb = fmaxf(0.f, dir.y) * 0.8f;
-        float glow = expf(-fabsf(dir.y) * 4.f) * 0.3f;
-        float ground = fmaxf(0.f, -dir.y * 0.5f);
-        float cloud = fmaxf(0.f, perlin_noise(sc.perm, dir.x * 10.f, dir.y * 3.f + 2.f, dir.z * 10.f) * 0.8f + 0.2f);
-        float cl = cloud * fmaxf(0.f, dir.y) * 0.5f;
-        return f3((0.4f * hb + 1.0f * glow + 0.1f * ground + 1.0f * sun + 0.9f * cl) * I,
-                  (0.7f * hb + 0.8f * glow + 0.15f * ground + 0.95f * sun + 0.9f * cl) * I,
-                  (1.0f * hb + 0.6f * glow + 0.1f * ground + 0.8f * sun + 1.0f * cl) * I);
+        for (int k = 0; k < 9; k++) s = __fmul_rn(s, s);
+        float sun = __fmul_rn(s, 10.f);
+        float hb = __fmul_rn(fmaxf(0.f, dir.y), 0.8f);
+        float glow = __fmul_rn(expf(__fmul_rn(fabsf(dir.y), -4.f)), 0.3f);
+        float ground = fmaxf(0.f, __fmul_rn(dir.y, -0.5f));
+        float cloud = fmaxf(0.f, fmaf(perlin_noise(sc.perm, __fmul_rn(dir.x, 10.f), fmaf(dir.y, 3.f, 2.f), __fmul_rn(dir.z, 10.f)), 0.8f, 0.2f));
+        float cl = __fmul_rn(__fmul_rn(cloud, fmaxf(0.f, dir.y)), 0.5f);
+        return f3(__fmul_rn(mix5(0.4f, hb, 1.0f, glow, 0.1f, ground, 1.0f, sun, 0.9f, cl), I),
+                  __fmul_rn(mix5(0.7f, hb, 0.8f, glow, 0.15f, ground, 0.95f, sun, 0.9f, cl), I),
+                  __fmul_rn(mix5(1.0f, hb, 0.6f, glow, 0.1f, ground, 0.8f, sun, 1.0f, cl), I));
     }
     default: {                                                                                                      // world.js:35-40
-        float t = 0.5f * (dir.y + 1.0f);
-        return f3(((1.0f - t) + 0.5f * t) * I, ((1.0f - t) + 0.7f * t) * I, ((1.0f - t) + 1.0f * t) * I);
+        float t = __fmul_rn(0.5f, __fadd_rn(dir.y, 1.0f));
+        // (1-t)*(1,1,1) + t*(0.5,0.7,1.0)
+        return f3(__fmul_rn(fmaf(t, 0.5f, __fsub_rn(1.0f, t)), I), __fmul_rn(fmaf(t, 0.7f, __fsub_rn(1.0f, t)), I), __fmul_rn(fmaf(t, 1.0f, __fsub_rn(1.0f, t)), I));
     }
     }
 }
@@ -541,11 +556,11 @@ __device__ inline float3 background(const DevScene& sc, float3 D) {
 // ------------------------------------------------------------------------------------------- sampling
 // math.js:22-31 by direct inversion (identical distributions; used by BRT_SAMPLER_FAST).
 __device__ __forceinline__ float3 uniform_sphere(float u0, float u1) {
-    float z = 1.f - 2.f * u0;
-    float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+    float z = fmaf(-2.f, u0, 1.f);
+    float r = sqrtf(fmaxf(0.f, fmaf(-z, z, 1.f)));
     float sn, cs;
-    sincospif(2.f * u1, &sn, &cs);
-    return f3(r * cs, r * sn, z);
+    sincospif(__fmul_rn(2.f, u1), &sn, &cs);
+    return f3(__fmul_rn(r, cs), __fmul_rn(r, sn), z);
 }
 
 }  // namespace brt

@@ -7,8 +7,11 @@
 namespace brt {
 
 constexpr int PT_BLOCK = 128;
-constexpr int PT_MIN_BLOCKS = 6;     // __launch_bounds__ min blocks/SM for the megakernel (<= 80 registers)
-constexpr int PT_COLD_SLOTS = 10;    // shared-memory words of cold per-path state per thread
+constexpr int PT_MIN_BLOCKS = 6;      // __launch_bounds__ min blocks/SM of the wavefront kernel (<= 80 registers)
+#ifndef PT_MIN_BLOCKS_MEGA
+#define PT_MIN_BLOCKS_MEGA 5          // megakernel: 96 registers, no spills in the traversal loop (6 -> 80 registers spills 120 B)
+#endif
+constexpr int PT_SLOT_WORDS = 13;    // shared-memory words per path slot (pathtrace.cu: SlotField; +1 for the sequential sampler)
 
 struct PTParams {
     DevScene sc;
@@ -19,14 +22,17 @@ struct PTParams {
     int aaMode;
     uint32_t seedLo, seedHi;
     int directLighting;
-    int stackSlots;              // shared-memory traversal-stack entries per thread (set by the launcher)
-    int refill;                  // megakernel: go back to shading when fewer than this many lanes of a warp still traverse
-    float4* accum;               // W*H fp32 RGBA sums (alpha = number of samples)
+    int wavefront;               // 0 = megakernel (one blocking traversal per thread), 1 = warp-local wavefront
+    int inflight;                // path slots per lane (samples of a pixel in flight): 1, 2, 3 or 4
+    int refill;                  // extend phase: idle lanes fetch the next queued ray once at least this many are idle
+    float4* accum;               // W*H fp32 RGBA sums (alpha = number of samples); with z chunks: planes of W*H each
+    size_t planeStride;          // float4 elements between the planes of consecutive z chunks (0 = single plane)
     unsigned long long* counters;// 8 x u64 (Counters), counting build only
 };
 
 // pathtrace.cu
 cudaError_t launch_pathtrace(const PTParams& p, int sampler, bool useBvh, bool count, int zSplit, cudaStream_t st);
+cudaError_t launch_sum_planes(float4* accum, const float4* planes, int nPlanes, size_t px, cudaStream_t st);
 cudaError_t launch_primary_aov(const PTParams& p, bool useBvh, int* objId, int* triId, float* t, float* nrm, unsigned char* front,
                                cudaStream_t st);
 cudaError_t launch_eval_background(const DevScene& sc, const float* dirs, int n, float* out, cudaStream_t st);

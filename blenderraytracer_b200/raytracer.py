@@ -358,6 +358,7 @@ class RayTracer:
         p.sampler, p.integrator, p.accel = L.SAMPLER[self.sampler], L.INTEGRATOR[self.integrator], L.ACCEL[self.accel]
         p.spp_batch, p.count_tests = int(self.sppBatch), 1 if self.countTests else 0
         p.refill_threshold = int(getattr(self, "refillThreshold", 0))
+        p.paths_in_flight = int(getattr(self, "pathsInFlight", 0))
         L.check(self._ctx, self._L.brt_set_render_params(self._ctx, C.byref(p)))
         return p
 

@@ -116,7 +116,7 @@ typedef struct brt_camera {
 typedef struct brt_render_params {
     int32_t width, height;
     int32_t spp;                 /* this.samples; AA 'none' forces 1 sample (ray-tracer.js:201) */
-    int32_t max_depth;           /* this.maxBounces: at most this many intersections per path (ray-tracer.js:103) */
+    int32_t max_depth;           /* this.maxBounces: at most this many intersections per path (ray-tracer.js:103); 0..250 */
     int32_t aa_mode;             /* BRT_AA_* */
     int32_t tonemap;             /* BRT_TONEMAP_* */
     double exposure, gamma;
@@ -130,8 +130,8 @@ typedef struct brt_render_params {
     int32_t accel;               /* BRT_ACCEL_* */
     int32_t spp_batch;           /* samples per launch between progress callbacks / cancel polls; 0 = auto */
     int32_t count_tests;         /* 1 = counting build of the same traversal (fills brt_stats.tests_*) */
-    int32_t refill_threshold;    /* megakernel tuning: warps return to shading when fewer lanes than this still traverse; 0 = default */
-    int32_t _pad1;
+    int32_t refill_threshold;    /* tuning: idle lanes of a warp fetch the next queued ray once this many are idle; 0 = default (8) */
+    int32_t paths_in_flight;     /* tuning: samples of a pixel in flight per lane (1..4); 0 = default (2) */
 } brt_render_params;
 
 typedef struct brt_scene_info {

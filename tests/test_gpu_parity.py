@@ -88,6 +88,8 @@ def test_primary_aov_f32(brt, name, accel):
     assert rel.max() <= 1e-5, f"max relative t error {rel.max():.3e}"
     dn = np.abs(a["normal"][ok].astype(np.float64) - o["normal"][ok]).max()
     assert dn <= 1e-5, f"max normal error {dn:.3e}"
+    # primary hits are evaluated in float64 in the reference's operation order: t is the reference's t rounded to fp32
+    assert np.array_equal(a["t"][ok], o["t"][ok].astype(np.float32))
     assert np.array_equal(a["front_face"][ok], o["front_face"][ok])
     miss = ~mism & (o["obj_id"] < 0)
     assert np.all(np.isinf(a["t"][miss]))

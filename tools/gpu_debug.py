@@ -24,6 +24,17 @@ def aov_diff(scene, W, H, accel="bvh"):
 
 def bvh_vs_brute(scene, W, H):
     rt = brt.RayTracer(W, H, seed=5); assert rt.loadFromJSON(scene)
+    aov = {}
+    for accel in ("brute", "bvh"):
+        rt.accel = accel
+        aov[accel] = rt.primaryAOV(32)
+    for key in ("obj_id", "tri_id", "t", "normal", "front_face"):
+        d = aov["brute"][key] != aov["bvh"][key]
+        if d.ndim == 3: d = d.any(axis=-1)
+        print(f"  aov {key}: {int(d.sum())} differ")
+        ys, xs = np.nonzero(d)
+        for y, x in list(zip(ys, xs))[:5]:
+            print(f"    px ({x},{y}) brute obj {aov['brute']['obj_id'][y,x]} tri {aov['brute']['tri_id'][y,x]} t {aov['brute']['t'][y,x]:.9g} | bvh obj {aov['bvh']['obj_id'][y,x]} tri {aov['bvh']['tri_id'][y,x]} t {aov['bvh']['t'][y,x]:.9g}")
     rt.updateRenderSettings(dict(samples=4, maxBounces=6)); rt.sampler = "reference"
     out = {}
     for accel in ("brute", "bvh"):
@@ -36,5 +47,9 @@ def bvh_vs_brute(scene, W, H):
         print(f"  px ({x},{y}) brute {out['brute'][y,x]} bvh {out['bvh'][y,x]}")
 
 if __name__ == "__main__":
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_parity as T
     print("c4 cornell"); aov_diff(gen_scenes.cornell("hdri"), 480, 270)
     print("c5 small"); bvh_vs_brute(gen_scenes.terrain(quads=24, extent=200.0), 320, 180)
+    print("ties"); bvh_vs_brute(T._tie_scene(), 360, 240); aov_diff(T._tie_scene(), 360, 240)
+    print("sample_mesh"); bvh_vs_brute(json.load(open(os.path.join(ROOT, "tests/golden/sample_mesh.json"))), 1280, 720)
