@@ -1,0 +1,86 @@
+/* Minimal declaration of the stable Node-API (N-API v4) surface used by brt_addon.c.
+ *
+ * The build image has no Node.js (no `node`, no node_api.h), so the addon is compiled against these prototypes as a
+ * syntax / ABI check and cannot be loaded here.  With a Node toolchain present, brt_addon.c includes the real
+ * <node_api.h> instead (see the __has_include test there) — the declarations below restate that header's C ABI for the
+ * functions we call and nothing else. */
+#ifndef BRT_NODE_API_MIN_H
+#define BRT_NODE_API_MIN_H
+#include <stddef.h>
+#include <stdint.h>
+#include <stdbool.h>
+
+typedef enum {
+    napi_ok, napi_invalid_arg, napi_object_expected, napi_string_expected, napi_name_expected, napi_function_expected,
+    napi_number_expected, napi_boolean_expected, napi_array_expected, napi_generic_failure, napi_pending_exception,
+    napi_cancelled, napi_escape_called_twice, napi_handle_scope_mismatch, napi_callback_scope_mismatch, napi_queue_full,
+    napi_closing, napi_bigint_expected, napi_date_expected, napi_arraybuffer_expected, napi_detachable_arraybuffer_expected,
+    napi_would_deadlock
+} napi_status;
+typedef enum { napi_undefined, napi_null, napi_boolean, napi_number, napi_string, napi_symbol, napi_object, napi_function,
+               napi_external, napi_bigint } napi_valuetype;
+typedef enum { napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array, napi_int32_array,
+               napi_uint32_array, napi_float32_array, napi_float64_array, napi_bigint64_array, napi_biguint64_array } napi_typedarray_type;
+typedef enum { napi_tsfn_release, napi_tsfn_abort } napi_threadsafe_function_release_mode;
+typedef enum { napi_tsfn_nonblocking, napi_tsfn_blocking } napi_threadsafe_function_call_mode;
+
+typedef struct napi_env__* napi_env;
+typedef struct napi_value__* napi_value;
+typedef struct napi_ref__* napi_ref;
+typedef struct napi_callback_info__* napi_callback_info;
+typedef struct napi_deferred__* napi_deferred;
+typedef struct napi_async_work__* napi_async_work;
+typedef struct napi_threadsafe_function__* napi_threadsafe_function;
+typedef napi_value (*napi_callback)(napi_env env, napi_callback_info info);
+typedef void (*napi_finalize)(napi_env env, void* finalize_data, void* finalize_hint);
+typedef void (*napi_async_execute_callback)(napi_env env, void* data);
+typedef void (*napi_async_complete_callback)(napi_env env, napi_status status, void* data);
+typedef void (*napi_threadsafe_function_call_js)(napi_env env, napi_value js_callback, void* context, void* data);
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+napi_status napi_get_cb_info(napi_env env, napi_callback_info cbinfo, size_t* argc, napi_value* argv, napi_value* this_arg, void** data);
+napi_status napi_create_function(napi_env env, const char* utf8name, size_t length, napi_callback cb, void* data, napi_value* result);
+napi_status napi_set_named_property(napi_env env, napi_value object, const char* utf8name, napi_value value);
+napi_status napi_get_named_property(napi_env env, napi_value object, const char* utf8name, napi_value* result);
+napi_status napi_has_named_property(napi_env env, napi_value object, const char* utf8name, bool* result);
+napi_status napi_create_external(napi_env env, void* data, napi_finalize finalize_cb, void* finalize_hint, napi_value* result);
+napi_status napi_get_value_external(napi_env env, napi_value value, void** result);
+napi_status napi_get_value_int32(napi_env env, napi_value value, int32_t* result);
+napi_status napi_get_value_double(napi_env env, napi_value value, double* result);
+napi_status napi_get_value_bool(napi_env env, napi_value value, bool* result);
+napi_status napi_get_value_string_utf8(napi_env env, napi_value value, char* buf, size_t bufsize, size_t* result);
+napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type, size_t* length, void** data,
+                                     napi_value* arraybuffer, size_t* byte_offset);
+napi_status napi_typeof(napi_env env, napi_value value, napi_valuetype* result);
+napi_status napi_create_object(napi_env env, napi_value* result);
+napi_status napi_create_int32(napi_env env, int32_t value, napi_value* result);
+napi_status napi_create_double(napi_env env, double value, napi_value* result);
+napi_status napi_get_boolean(napi_env env, bool value, napi_value* result);
+napi_status napi_create_string_utf8(napi_env env, const char* str, size_t length, napi_value* result);
+napi_status napi_get_undefined(napi_env env, napi_value* result);
+napi_status napi_create_error(napi_env env, napi_value code, napi_value msg, napi_value* result);
+napi_status napi_throw_error(napi_env env, const char* code, const char* msg);
+napi_status napi_create_promise(napi_env env, napi_deferred* deferred, napi_value* promise);
+napi_status napi_resolve_deferred(napi_env env, napi_deferred deferred, napi_value resolution);
+napi_status napi_reject_deferred(napi_env env, napi_deferred deferred, napi_value rejection);
+napi_status napi_create_reference(napi_env env, napi_value value, uint32_t initial_refcount, napi_ref* result);
+napi_status napi_delete_reference(napi_env env, napi_ref ref);
+napi_status napi_call_function(napi_env env, napi_value recv, napi_value func, size_t argc, const napi_value* argv, napi_value* result);
+napi_status napi_create_async_work(napi_env env, napi_value async_resource, napi_value async_resource_name,
+                                   napi_async_execute_callback execute, napi_async_complete_callback complete, void* data,
+                                   napi_async_work* result);
+napi_status napi_queue_async_work(napi_env env, napi_async_work work);
+napi_status napi_delete_async_work(napi_env env, napi_async_work work);
+napi_status napi_create_threadsafe_function(napi_env env, napi_value func, napi_value async_resource, napi_value async_resource_name,
+                                            size_t max_queue_size, size_t initial_thread_count, void* thread_finalize_data,
+                                            napi_finalize thread_finalize_cb, void* context, napi_threadsafe_function_call_js call_js_cb,
+                                            napi_threadsafe_function* result);
+napi_status napi_call_threadsafe_function(napi_threadsafe_function func, void* data, napi_threadsafe_function_call_mode is_blocking);
+napi_status napi_release_threadsafe_function(napi_threadsafe_function func, napi_threadsafe_function_release_mode mode);
+#ifdef __cplusplus
+}
+#endif
+#define NAPI_AUTO_LENGTH SIZE_MAX
+#endif

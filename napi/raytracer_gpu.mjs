@@ -1,0 +1,123 @@
+// raytracer_gpu.mjs — drop-in GPU render for the reference's RayTracer (js/ray-tracer.js).
+//
+//   import { RayTracer } from '../js/ray-tracer.js';
+//   import { installGpuRender } from './napi/raytracer_gpu.mjs';
+//   installGpuRender(RayTracer);            // RayTracer.prototype.render now runs on the B200 through libbrt
+//
+// Everything above render() stays the reference's own code: scene-loader.js builds the World, camera.js builds the
+// Camera, the UI setters mutate the settings.  This shim only FLATTENS those live objects (world.js:9-18,
+// geometry.js, materials.js, lights.js, camera.js:14-35) into the typed arrays brt_addon.c takes and keeps the
+// observable contract of render(onProgress) (ray-tracer.js:166-281): imageData.data is filled (row 0 = top, alpha 255),
+// putImageData is called, onProgress(fraction) fires and ends with 1.0, window.renderCancelled stops the render without
+// the final blit.  The image is written by the GPU directly into imageData.data's backing store.
+//
+// NOTE: this image has no Node.js, so this file and brt_addon.node have not been executed here; the same C ABI is
+// exercised end to end by the Python ctypes binding (blenderraytracer_b200/) and its tests.
+import { createRequire } from 'node:module';
+const require = createRequire(import.meta.url);
+const addon = require('./brt_addon.node');
+
+const OBJ = { Sphere: 0, Plane: 1, Box: 2, Triangle: 3, TriangleMesh: 4 };
+const MAT = { Lambertian: 0, Metal: 1, Dielectric: 2, Emissive: 3 };
+const AA = { none: 0, supersampling: 1, stochastic: 2 };            // any other string: pixel-centre samples (3)
+const TONEMAP = { reinhard: 0, aces: 1, linear: 2 };
+const CAM = { perspective: 0, orthographic: 1 };                     // any other string: 2 (camera.js:25 vs :39)
+
+const v3 = (v) => [v.x, v.y, v.z];
+
+// world.objects / world.lights -> rows (one per object, IN ORDER: the row index is the object ID, world.js:24-30)
+export function flattenWorld(world) {
+  const objects = [], materials = [], tris = [], lights = [];
+  let firstTri = 0;
+  for (const o of world.objects) {
+    const kind = o.constructor.name;
+    const m = o.material, mk = m.constructor.name;
+    const color = mk === 'Emissive' ? m.color : (mk === 'Dielectric' ? { x: 1, y: 1, z: 1 } : m.albedo);
+    const param = mk === 'Metal' ? m.roughness : mk === 'Dielectric' ? m.refractionIndex : mk === 'Emissive' ? m.intensity : 0;
+    if (!(mk in MAT)) throw new Error(`unsupported material ${mk} (textured materials are never instantiated by the reference)`);
+    materials.push(MAT[mk], ...v3(color), param);
+    const mat = materials.length / 5 - 1;
+    const z = [0, 0, 0];
+    if (kind === 'Sphere') objects.push(OBJ.Sphere, mat, ...v3(o.center), o.radius, 0, 0, ...z, 0, 0);
+    else if (kind === 'Plane') objects.push(OBJ.Plane, mat, ...v3(o.point), ...v3(o.normal), ...z, 0, 0);
+    else if (kind === 'Box') objects.push(OBJ.Box, mat, ...v3(o.min), ...v3(o.max), ...z, 0, 0);
+    else if (kind === 'Triangle') objects.push(OBJ.Triangle, mat, ...v3(o.v0), ...v3(o.v1), ...v3(o.v2), 0, 0);
+    else if (kind === 'TriangleMesh') {
+      // o.triangles is already post-filter (geometry.js:206-231): its order defines the triangle IDs
+      for (const t of o.triangles) tris.push(...v3(t.v0), ...v3(t.v1), ...v3(t.v2));
+      objects.push(OBJ.TriangleMesh, mat, ...z, ...z, ...z, firstTri, o.triangles.length);
+      firstTri += o.triangles.length;
+    } else throw new Error(`unsupported object ${kind}`);
+  }
+  for (const l of world.lights) {
+    const point = l.constructor.name === 'PointLight';
+    lights.push(point ? 0 : 1, ...v3(point ? l.position : l.direction), ...v3(l.color), l.intensity);
+  }
+  return { objects: new Float64Array(objects), materials: new Float64Array(materials), tris: new Float64Array(tris), lights: new Float64Array(lights) };
+}
+
+// the Camera object's own derived members (camera.js:14-35): no libm call is repeated on the native side
+export function flattenCamera(c) {
+  return new Float64Array([...v3(c.origin), ...v3(c.lowerLeftCorner), ...v3(c.horizontal), ...v3(c.vertical),
+    ...v3(c.u), ...v3(c.v), ...v3(c.w), c.lensRadius, c.type in CAM ? CAM[c.type] : 2]);
+}
+
+// world.background is a closure and cannot cross a C ABI: the wrappers below remember which factory installed it;
+// a bound skyGradient / proceduralSky can still be recognised by name.
+function backgroundOf(rt) {
+  const w = rt.world, bg = w.background;
+  if (rt._brtBackground) return rt._brtBackground;                   // set by the updateBackground wrapper
+  if (bg === w.skyGradient || (bg && bg.name === 'bound skyGradient')) return { kind: 0, color: [0.1, 0.1, 0.1] };
+  if (bg && bg.name === 'bound proceduralSky') return { kind: 3, color: [0.1, 0.1, 0.1] };
+  return { kind: 0, color: [0.1, 0.1, 0.1] };
+}
+
+export function installGpuRender(RayTracer, { device = 0, seed = 1 } = {}) {
+  const origUpdateBackground = RayTracer.prototype.updateBackground;
+  RayTracer.prototype.updateBackground = function (type, intensity = 1.0) {       // ray-tracer.js:568-585
+    origUpdateBackground.call(this, type, intensity);
+    const kind = { solid: 1, hdri: 2, procedural_sky: 3 }[type] ?? 0;
+    this._brtBackground = { kind, color: [0.1, 0.1, 0.1] };
+  };
+  const origPreset = RayTracer.prototype.loadPreset;
+  RayTracer.prototype.loadPreset = function (name) {                              // ray-tracer.js:282-299: new World() => gradient
+    origPreset.call(this, name);
+    this._brtBackground = name === 'cornell' ? { kind: 1, color: [0, 0, 0] } : undefined;   // setupCornellBox (:424)
+  };
+  const origLoad = RayTracer.prototype.loadFromJSON;
+  RayTracer.prototype.loadFromJSON = function (json) {                            // ray-tracer.js:305-334
+    const ok = origLoad.call(this, json);
+    const t = json?.background?.type;
+    // deviation D1: the loader binds the solid / hdri FACTORIES (scene-loader.js:43,45 -> NaN -> black); we honour the intent
+    this._brtBackground = { kind: { solid: 1, hdri: 2, procedural_sky: 3 }[t] ?? 0, color: json?.background?.color ?? [0.1, 0.1, 0.1] };
+    return ok;
+  };
+
+  RayTracer.prototype.render = async function (onProgress) {                       // ray-tracer.js:166-281
+    this._brt ??= addon.create(device);
+    const ctx = this._brt;
+    const flat = flattenWorld(this.world);
+    addon.setSceneFlat(ctx, flat.objects, flat.materials, flat.tris, flat.lights);
+    addon.setCameraDerived(ctx, flattenCamera(this.camera));
+    const bg = backgroundOf(this);
+    const perm = this.world.cloudNoise ? Uint8Array.from(this.world.cloudNoise.p.slice(0, 256)) : undefined;
+    addon.setBackground(ctx, bg.kind, bg.color[0], bg.color[1], bg.color[2], this.world.skyIntensity, perm);
+    addon.setRenderParams(ctx, {
+      width: this.width, height: this.height, samples: this.samples, maxBounces: this.maxBounces,
+      aaMode: this.antiAliasing in AA ? AA[this.antiAliasing] : 3, toneMapping: TONEMAP[this.toneMapping] ?? 0,
+      exposure: this.exposure, gamma: this.gamma, denoising: this.denoising ? 1 : 0, denoiseStrength: this.denoiseStrength,
+      seed: seed + (this._brtFrame = (this._brtFrame ?? 0) + 1),     // Math.random is unseeded: a new stream per render
+    });
+    const poll = setInterval(() => { if (globalThis.window?.renderCancelled) addon.cancel(ctx); }, 50);   // :190,:256
+    try {
+      await addon.render(ctx, this.imageData.data, onProgress);
+    } catch (e) {
+      if (e.code === 'BRT_E_CANCELLED') return;                      // the reference stops without the final blit (:264)
+      throw e;
+    } finally {
+      clearInterval(poll);
+    }
+    this.ctx.putImageData(this.imageData, 0, 0);                     // :278
+  };
+  return RayTracer;
+}
