@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrt.so")
+LIB_PATH = os.environ.get("BRT_LIBBRT") or os.path.join(_HERE, "libbrt.so")   # BRT_LIBBRT: kernel-tuning experiments only
 
 BRT_OK, BRT_E_INVALID, BRT_E_CUDA, BRT_E_PARSE, BRT_E_NOSCENE, BRT_E_CANCELLED, BRT_E_NOMEM, BRT_E_STATE = 0, -1, -2, -3, -4, -5, -6, -7
 OBJ_SPHERE, OBJ_PLANE, OBJ_BOX, OBJ_TRIANGLE, OBJ_MESH = range(5)

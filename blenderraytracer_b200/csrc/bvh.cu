@@ -8,6 +8,9 @@
 // n3 = (child0, child1, 0, 0) bit patterns, LEAF_BIT | pid for leaves.
 #include "brt_kernels.h"
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace brt {
 
@@ -84,13 +87,17 @@ __device__ __forceinline__ uint32_t expand10(uint32_t v) {
     v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
     return v;
 }
-__global__ void k_morton(const Aabb* boxes, int n, const float* sb, uint32_t* keys, uint32_t* vals) {
+__global__ void k_morton(const Aabb* boxes, int n, const float* sb, int uniformScale, uint32_t* keys, uint32_t* vals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Aabb b = boxes[i];
     uint32_t q[3];
+    // uniformScale = 1: one scale for all three axes (the largest scene extent) — a thin axis, a terrain's height, then
+    // occupies few Morton cells and only splits at fine levels instead of cutting every third level through geometry that
+    // is flat there.  uniformScale = 0: every axis normalised to its own extent.  build_lbvh builds both, keeps the cheaper.
+    float extMax = fmaxf(sb[3] - sb[0], fmaxf(sb[4] - sb[1], sb[5] - sb[2]));
     for (int k = 0; k < 3; k++) {
-        float ext = sb[3 + k] - sb[k];
+        float ext = uniformScale ? extMax : sb[3 + k] - sb[k];
         float x = ext > 0.f ? (0.5f * (b.mn[k] + b.mx[k]) - sb[k]) / ext : 0.f;
         q[k] = (uint32_t)fminf(fmaxf(x * 1024.f, 0.f), 1023.f);
     }
@@ -239,6 +246,23 @@ __global__ void k_refit(const DevScene sc, int n, const uint32_t* sortedPrim, co
     }
 }
 
+// Surface-area cost of a hierarchy: sum of the internal nodes' box areas (leaves hold one primitive each, so the leaf term
+// is the same for every candidate tree).  Per-block partial sums, folded on the host in fixed order (deterministic choice).
+__global__ void __launch_bounds__(256) k_sah_cost(const Aabb* nodeBox, int nInternal, double* blockSums) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double a = 0.0;
+    if (i < nInternal) {
+        Aabb b = nodeBox[i];
+        double dx = (double)b.mx[0] - b.mn[0], dy = (double)b.mx[1] - b.mn[1], dz = (double)b.mx[2] - b.mn[2];
+        a = dx * dy + dy * dz + dz * dx;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = red[0];
+}
+
 #define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return e_; } } while (0)
 
 cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st) {
@@ -247,13 +271,13 @@ cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st)
     if (n < 2) return cudaSuccess;                    // 0 or 1 bounded primitive: traversal falls back to the linear loop
     Aabb *boxes = nullptr, *nodeBox = nullptr; float *blockBounds = nullptr, *sb = nullptr;
     uint32_t *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr, *hist = nullptr; unsigned int* flags = nullptr;
-    int2* children = nullptr; int *parent = nullptr, *nodeDepth = nullptr; float4* nodes = nullptr;
+    int2* children = nullptr; int *parent = nullptr, *nodeDepth = nullptr; float4 *nodes = nullptr, *nodesAlt = nullptr; double* blockSums = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     bool ok = false;
     auto cleanup = [&]() {
         if (!ok) cudaFree(nodes);
         cudaFree(boxes); cudaFree(nodeBox); cudaFree(blockBounds); cudaFree(sb); cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
-        cudaFree(hist); cudaFree(flags); cudaFree(children); cudaFree(parent); cudaFree(nodeDepth);
+        cudaFree(hist); cudaFree(flags); cudaFree(children); cudaFree(parent); cudaFree(nodeDepth); cudaFree(nodesAlt); cudaFree(blockSums);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
@@ -264,28 +288,47 @@ cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st)
     BVH_CK(cudaMalloc(&hist, 4 * 256 * (size_t)sortBlocks)); BVH_CK(cudaMalloc(&flags, 4 * (size_t)(n - 1)));
     BVH_CK(cudaMalloc(&children, sizeof(int2) * (n - 1))); BVH_CK(cudaMalloc(&parent, 4 * (size_t)(2 * n - 1)));
     BVH_CK(cudaMalloc(&nodeDepth, 4 * (size_t)(n - 1)));
-    BVH_CK(cudaMalloc(&nodes, sizeof(float4) * 4 * (size_t)(n - 1)));
+    BVH_CK(cudaMalloc(&nodes, sizeof(float4) * 4 * (size_t)(n - 1))); BVH_CK(cudaMalloc(&nodesAlt, sizeof(float4) * 4 * (size_t)(n - 1)));
+    BVH_CK(cudaMalloc(&blockSums, sizeof(double) * ((n - 1 + 255) / 256)));
     BVH_CK(cudaEventCreate(&e0)); BVH_CK(cudaEventCreate(&e1));
     BVH_CK(cudaEventRecord(e0, st));
     k_prim_bounds<<<nb, 256, 0, st>>>(sc, n, boxes, blockBounds);
     k_scene_bounds<<<1, 256, 0, st>>>(blockBounds, nb, sb);
-    k_morton<<<nb, 256, 0, st>>>(boxes, n, sb, k0, v0);
-    uint32_t *ki = k0, *ko = k1, *vi = v0, *vo = v1;
-    for (int shift = 0; shift < 32; shift += 8) {
-        k_sort_hist<<<sortBlocks, SORT_THREADS, 0, st>>>(ki, n, shift, hist, sortBlocks);
-        k_sort_scan<<<1, 1024, 0, st>>>(hist, 256 * sortBlocks);
-        k_sort_scatter<<<sortBlocks, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, hist, sortBlocks);
-        uint32_t* t = ki; ki = ko; ko = t; t = vi; vi = vo; vo = t;
+    // two candidate hierarchies (Morton quantisation per axis / uniform); the one with the smaller surface-area cost is kept
+    const int costBlocks = (n - 1 + 255) / 256;
+    std::vector<double> hostSums(costBlocks);
+    double bestCost = 0.0; int bestMode = -1, bestDepth = 0;
+    for (int mode = 0; mode < 2; mode++) {
+        float4* target = mode == 0 ? nodes : nodesAlt;
+        k_morton<<<nb, 256, 0, st>>>(boxes, n, sb, mode, k0, v0);
+        uint32_t *ki = k0, *ko = k1, *vi = v0, *vo = v1;
+        for (int shift = 0; shift < 32; shift += 8) {
+            k_sort_hist<<<sortBlocks, SORT_THREADS, 0, st>>>(ki, n, shift, hist, sortBlocks);
+            k_sort_scan<<<1, 1024, 0, st>>>(hist, 256 * sortBlocks);
+            k_sort_scatter<<<sortBlocks, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, hist, sortBlocks);
+            uint32_t* t = ki; ki = ko; ko = t; t = vi; vi = vo; vo = t;
+        }
+        BVH_CK(cudaMemsetAsync(flags, 0, 4 * (size_t)(n - 1), st));
+        k_karras<<<(n - 1 + 255) / 256, 256, 0, st>>>(ki, n, children, parent);
+        k_refit<<<nb, 256, 0, st>>>(sc, n, vi, boxes, children, parent, nodeBox, nodeDepth, flags, target);
+        k_sah_cost<<<costBlocks, 256, 0, st>>>(nodeBox, n - 1, blockSums);
+        BVH_CK(cudaMemcpyAsync(hostSums.data(), blockSums, sizeof(double) * costBlocks, cudaMemcpyDeviceToHost, st));
+        int depth = 0;
+        BVH_CK(cudaMemcpyAsync(&depth, nodeDepth, 4, cudaMemcpyDeviceToHost, st));
+        BVH_CK(cudaStreamSynchronize(st));
+        double cost = 0.0;
+        for (double v : hostSums) cost += v;
+        if (getenv("BRT_DEBUG")) fprintf(stderr, "[brt] lbvh candidate %d: sah cost %.6g depth %d\n", mode, cost, depth);
+        // the surface-area estimate assumes uniformly distributed rays; differences of a few percent are not predictive
+        // (measured: C3 2 % apart, slower tree estimated cheaper), so the uniform-scale tree must win by > 10 % to be taken
+        if (bestMode < 0 || cost < 0.9 * bestCost) { bestCost = cost; bestMode = mode; bestDepth = depth; }
     }
-    BVH_CK(cudaMemsetAsync(flags, 0, 4 * (size_t)(n - 1), st));
-    k_karras<<<(n - 1 + 255) / 256, 256, 0, st>>>(ki, n, children, parent);
-    k_refit<<<nb, 256, 0, st>>>(sc, n, vi, boxes, children, parent, nodeBox, nodeDepth, flags, nodes);
+    if (bestMode == 1) { float4* t = nodes; nodes = nodesAlt; nodesAlt = t; }
     BVH_CK(cudaEventRecord(e1, st));
     BVH_CK(cudaGetLastError());
     BVH_CK(cudaEventSynchronize(e1));
     float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
-    int depth = 0;
-    BVH_CK(cudaMemcpy(&depth, nodeDepth, 4, cudaMemcpyDeviceToHost));
+    int depth = bestDepth;
     ok = true;
     cleanup();
     out->nodes = nodes; out->nNodes = n - 1; out->depth = depth; out->buildMs = ms;

@@ -1,0 +1,175 @@
+"""Edge cases of the hot path on the GPU (-m gpu), each checked against the float64 oracle: empty and degenerate scenes,
+scenes with no / one / two bounded primitives (no BVH, trivial BVH), ragged image sizes, axis-parallel rays, cameras inside
+objects, negative radii, the reference's presets built object by object, ragged meshes."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def brt():
+    import blenderraytracer_b200 as b
+    return b
+
+
+CAM = dict(position=[0, 1, 4], lookAt=[0, 0, 0], fov=45, aspect=1.5, aperture=0.0, focusDist=4.0)
+LAM = dict(type="lambertian", color=[0.6, 0.5, 0.4])
+
+
+def _check(brt, scene, W=150, H=100, spp=4, depth=5, max_id_mismatch=2, accels=("brute", "bvh")):
+    """AOV f64 bit-exact, AOV f32 IDs / t / normal, and a same-stream render within 2 LSB, for every accel mode."""
+    from oracle.oracle import OracleRayTracer
+    rt = brt.RayTracer(W, H, seed=31)
+    orc = OracleRayTracer(W, H, seed=31, threads=4)
+    assert rt.loadFromJSON(scene) and orc.loadFromJSON(scene)
+    for r in (rt, orc):
+        r.updateRenderSettings(dict(samples=spp, maxBounces=depth))
+    o = orc.primary_aov()
+    a64 = rt.primaryAOV(64)
+    for key in ("obj_id", "tri_id", "t", "normal", "front_face"):
+        assert np.array_equal(a64[key], o[key]), key
+    ref = orc.render()
+    rt.sampler = "reference"
+    for accel in accels:
+        rt.accel = accel
+        a = rt.primaryAOV(32)
+        mism = (a["obj_id"] != o["obj_id"]) | (a["tri_id"] != o["tri_id"])
+        assert mism.sum() <= max_id_mismatch, (accel, int(mism.sum()))
+        ok = ~mism & (o["obj_id"] >= 0)
+        if ok.any():
+            assert np.array_equal(a["t"][ok], o["t"][ok].astype(np.float32)), accel
+            assert np.abs(a["normal"][ok] - o["normal"][ok]).max() <= 1e-5, accel
+        img = rt.render()
+        d = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=-1)
+        assert (d <= 2).mean() >= 0.97, (accel, (d <= 2).mean())
+    return rt, orc
+
+
+def test_empty_world_is_background_only(brt):
+    for bg in ("gradient", "hdri", "procedural_sky", "solid"):
+        rt, orc = _check(brt, dict(objects=[], camera=CAM, background=dict(type=bg, intensity=0.8)))
+        assert np.all(rt.primaryAOV(32)["obj_id"] == -1)
+        assert rt.sceneInfo()["n_bvh_nodes"] == 0
+
+
+def test_only_unbounded_planes(brt):
+    scene = dict(objects=[dict(type="plane", point=[0, -1, 0], normal=[0, 1, 0], material=LAM),
+                          dict(type="plane", point=[0, 0, -6], normal=[0, 0, 1], material=dict(type="metal", color=[0.9, 0.9, 0.9], roughness=0.0))],
+                 camera=CAM, background=dict(type="gradient"))
+    rt, _ = _check(brt, scene)
+    assert rt.sceneInfo()["n_bvh_nodes"] == 0
+
+
+def test_one_and_two_bounded_primitives(brt):
+    one = dict(objects=[dict(type="sphere", center=[0, 0, 0], radius=1.0, material=LAM)], camera=CAM, background=dict(type="gradient"))
+    rt, _ = _check(brt, one)
+    assert rt.sceneInfo()["n_bvh_nodes"] == 0                       # a single primitive needs no hierarchy
+    two = dict(objects=one["objects"] + [dict(type="box", min=[1.2, -1, -1], max=[2.2, 0.5, 0.3], material=LAM)], camera=CAM)
+    rt, _ = _check(brt, two)
+    assert rt.sceneInfo()["n_bvh_nodes"] == 1
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (37, 19), (16, 8), (17, 9), (255, 3)])
+def test_ragged_image_sizes(brt, sample_scene, W, H):
+    _check(brt, sample_scene, W, H)
+
+
+def test_axis_parallel_rays_and_box_faces(brt):
+    """Odd image size + symmetric camera: the centre column / row have direction components that are exactly 0
+    (division by zero inside the slab test: +-inf / NaN semantics of geometry.js:86-103)."""
+    scene = dict(objects=[dict(type="box", min=[-1, -1, -1], max=[1, 1, 1], material=LAM),
+                          dict(type="box", min=[-3, -0.5, -0.5], max=[-2, 0.5, 0.5], material=LAM),
+                          dict(type="plane", point=[0, -1, 0], normal=[0, 1, 0], material=LAM)],
+                 camera=dict(position=[0, 0, 5], lookAt=[0, 0, 0], fov=50, aspect=1.0, aperture=0.0, focusDist=5.0),
+                 background=dict(type="gradient"))
+    _check(brt, scene, 101, 101, max_id_mismatch=8)
+
+
+def test_camera_inside_objects(brt):
+    inside_sphere = dict(objects=[dict(type="sphere", center=[0, 0, 0], radius=10.0, material=dict(type="emissive", color=[1, 0.9, 0.8], intensity=0.5)),
+                                  dict(type="sphere", center=[0, 0, -2], radius=0.7, material=dict(type="dielectric", ior=1.5))],
+                         camera=dict(position=[0, 0, 2], lookAt=[0, 0, -2], fov=50, aspect=1.5, aperture=0.0, focusDist=4.0))
+    rt, orc = _check(brt, inside_sphere, depth=8)
+    assert rt.primaryAOV(64)["front_face"].min() == 0               # the big sphere is seen from inside
+    inside_box = dict(objects=[dict(type="box", min=[-3, -2, -6], max=[3, 2, 3], material=LAM),
+                               dict(type="sphere", center=[0, 1.5, -2], radius=0.3, material=dict(type="emissive", color=[1, 1, 1], intensity=20))],
+                      camera=dict(position=[0, 0, 2], lookAt=[0, 0, -2], fov=60, aspect=1.5, aperture=0.0, focusDist=4.0))
+    _check(brt, inside_box, depth=6)
+
+
+def test_negative_radius_hollow_glass(brt):
+    """Sphere(center, -0.45, glass) inside Sphere(center, 0.5, glass): the hollow-glass idiom (ray-tracer.js:347)."""
+    g = dict(type="dielectric", ior=1.5)
+    scene = dict(objects=[dict(type="sphere", center=[0, 0, -1], radius=0.5, material=g), dict(type="sphere", center=[0, 0, -1], radius=-0.45, material=g),
+                          dict(type="plane", point=[0, -0.5, 0], normal=[0, 1, 0], material=LAM)],
+                 camera=dict(position=[0, 0.3, 1.2], lookAt=[0, 0, -1], fov=40, aspect=1.5, aperture=0.0, focusDist=2.2), background=dict(type="gradient"))
+    _check(brt, scene, depth=10)
+
+
+def test_degenerate_and_ragged_meshes(brt):
+    verts = [[-1, 0, 0], [1, 0, 0], [0, 1.5, 0], [0, 0.5, 0], [2, 2, -1]]
+    idx = [0, 1, 2,   0, 0, 0,   0, 1, 1,   3, 3, 4,   0, 1]            # one real triangle, three zero-area ones, an incomplete tail
+    scene = dict(objects=[dict(type="mesh", vertices=verts, indices=idx, material=LAM),
+                          dict(type="mesh", vertices=verts, indices=[], material=LAM),          # a mesh with no triangles is still object 1
+                          dict(type="triangle", v0=[2, 0, 0], v1=[2, 0, 0], v2=[2, 0, 0], material=LAM),
+                          dict(type="sphere", center=[-2, 0.5, 0], radius=0.5, material=LAM)],
+                 camera=CAM, background=dict(type="gradient"))
+    rt, orc = _check(brt, scene)
+    a = rt.primaryAOV(64)
+    assert set(np.unique(a["obj_id"])) == {-1, 0, 3} and set(np.unique(a["tri_id"][a["obj_id"] == 0])) == {0}
+    assert rt.sceneInfo()["n_triangles"] == 5
+
+
+@pytest.mark.parametrize("preset", ["default", "glass", "metal", "cornell"])
+def test_presets_built_object_by_object(brt, preset):
+    """loadPreset (ray-tracer.js:282-299, 42-77, 336-435): scenes built through World.add / brt_scene_set_flat rather than JSON."""
+    from oracle.oracle import OracleRayTracer
+    W, H = 180, 120
+    rt = brt.RayTracer(W, H, seed=8)
+    orc = OracleRayTracer(W, H, seed=8, threads=4)
+    rt.loadPreset(preset)
+    orc.loadPreset(preset)
+    o, a64 = orc.primary_aov(), rt.primaryAOV(64)
+    for key in ("obj_id", "t", "normal", "front_face"):
+        assert np.array_equal(a64[key], o[key]), key
+    for r in (rt, orc):
+        r.updateRenderSettings(dict(samples=4, maxBounces=6))
+    rt.sampler = "reference"
+    img, ref = rt.render(), orc.render()
+    d = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=-1)
+    assert (d <= 2).mean() >= 0.96, (d <= 2).mean()
+
+
+def test_camera_presets_and_ui_setters(brt, sample_scene):
+    """updateCamera / loadCameraPreset / resizeCanvas (ray-tracer.js:475-510, 598-680) keep the two mirrors in step."""
+    from oracle.oracle import OracleRayTracer
+    rt, orc = brt.RayTracer(120, 80), OracleRayTracer(120, 80)
+    for r in (rt, orc):
+        assert r.loadFromJSON(sample_scene)
+        assert r.loadCameraPreset("close-up") and not r.loadCameraPreset("nope")
+        r.updateCamera(dict(fov=55, aperture=0))          # aperture 0 is falsy: keeps the preset's 0.02 (`||`)
+        r.resizeCanvas(200, 100)
+    cg, co = rt.camera, orc.scene.camera()
+    for key in ("origin", "lowerLeftCorner", "horizontal", "vertical", "u", "v", "w"):
+        np.testing.assert_allclose(cg[key], co[key], rtol=0, atol=1e-14, err_msg=key)
+    assert cg["lensRadius"] == co["lensRadius"] == 0.01
+    assert np.array_equal(rt.primaryAOV(64)["t"], orc.primary_aov()["t"])
+
+
+def test_depth_of_field_statistics(brt, sample_scene):
+    """Thin lens (aperture 0.05 in the fixture, camera.js:44-48): blurred edges agree statistically with the oracle."""
+    from oracle.oracle import OracleRayTracer
+    sc = json.loads(json.dumps(sample_scene))
+    sc["camera"]["aperture"] = 0.4
+    W, H, spp = 150, 100, 64
+    rt = brt.RayTracer(W, H, seed=3); orc = OracleRayTracer(W, H, seed=4, threads=8); orc2 = OracleRayTracer(W, H, seed=5, threads=8)
+    for r in (rt, orc, orc2):
+        assert r.loadFromJSON(sc)
+        r.updateRenderSettings(dict(samples=spp, maxBounces=4))
+    rt.render(); orc.render(); orc2.render()
+    g, a, b = (x.floatData[..., :3].astype(np.float64) for x in (rt, orc, orc2))
+    assert np.sqrt(np.mean((g - a) ** 2)) <= 1.5 * np.sqrt(np.mean((b - a) ** 2)) + 1e-4
+    assert np.abs((g - a).mean(axis=(0, 1))).max() <= 3e-3
