@@ -34,6 +34,22 @@ __device__ __forceinline__ void camera_ray64(const DevCamera& c, int W, int H, i
     }
 }
 
+// fp32 form of the same ray (BRT_SAMPLER_FAST render path: jittered, lens-offset camera samples have no float64 reference
+// to match bit for bit; LLC - origin is formed in float64 on the host side of this call and rounded once).
+__device__ __forceinline__ void camera_ray32(const DevCamera& c, int W, int H, int aaMode, int col, int jUp, CamSample cs, float3& O, float3& D) {
+    float u, v;
+    if (aaMode == 1) { u = __fdiv_rn((float)col + cs.s, (float)W); v = __fdiv_rn((float)jUp + cs.t, (float)H); }
+    else if (aaMode == 2) { u = __fdiv_rn(fmaf(cs.s, 0.5f, (float)col + 0.5f), (float)W); v = __fdiv_rn(fmaf(cs.t, 0.5f, (float)jUp + 0.5f), (float)H); }
+    else { u = __fdiv_rn((float)col + 0.5f, (float)W); v = __fdiv_rn((float)jUp + 0.5f, (float)H); }
+    float rx = __fmul_rn(cs.dx, (float)c.lensRadius), ry = __fmul_rn(cs.dy, (float)c.lensRadius);
+    float3 off = madd(f3((float)c.cv[0], (float)c.cv[1], (float)c.cv[2]), ry, f3((float)c.cu[0], (float)c.cu[1], (float)c.cu[2]) * rx);
+    O = f3((float)c.o[0], (float)c.o[1], (float)c.o[2]) + off;
+    // D = (LLC - origin) + u*H + v*V - off
+    float3 llo = f3((float)(c.ll[0] - c.o[0]), (float)(c.ll[1] - c.o[1]), (float)(c.ll[2] - c.o[2]));
+    D = madd(f3((float)c.v[0], (float)c.v[1], (float)c.v[2]), v, madd(f3((float)c.h[0], (float)c.h[1], (float)c.h[2]), u, llo)) - off;
+    if (c.type == 1) D = normalize0(D - f3((float)c.cw[0], (float)c.cw[1], (float)c.cw[2]));
+}
+
 template <int SAMPLER>
 __device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t pix, uint32_t s, RngSeq& rng) {
     CamSample cs; cs.s = 0.f; cs.t = 0.f;
@@ -355,6 +371,13 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
     const int row = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = col < p.W && row < p.H;
     const DevScene& sc = p.sc;
+    // float64 primary rays + float64 evaluation of the primary hit: always with the sequential (reference) sampler — the mode
+    // that is compared sample for sample with the float64 oracle — and in the AOV kernel; the fast sampler is fp32 throughout
+#ifdef BRT_PRECISE_ALWAYS
+    constexpr bool PRECISE = true;
+#else
+    constexpr bool PRECISE = SAMPLER == 1;
+#endif
     Counters cnt = {};
     if (inside) {
         const int jUp = p.H - 1 - row;
@@ -375,9 +398,11 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 if (s >= sEnd) break;
                 cs = (uint32_t)s++;
                 cam = camera_sample<SAMPLER>(p, pix, cs, rng);
-                D3 O64, D64;
-                camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
-                O = tof3(O64); D = tof3(D64);
+                if (PRECISE) {
+                    D3 O64, D64;
+                    camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
+                    O = tof3(O64); D = tof3(D64);
+                } else camera_ray32(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                 beta = f3(1.f, 1.f, 1.f); self = PID_NONE; depth = 0; alive = true;
             }
             Hit h = trace<USE_BVH, COUNT, false>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK);
@@ -387,7 +412,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 continue;
             }
             Surface sf = make_surface(sc, h, O, D, self);
-            if (depth == 0) {                                                 // primary hit: float64 evaluation of the selected primitive
+            if (PRECISE && depth == 0) {                                      // primary hit: float64 evaluation of the selected primitive
                 D3 O64, D64; double t64;
                 camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
                 refine_primary(sc, h.pid, O64, D64, t64, sf);
