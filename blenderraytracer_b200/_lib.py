@@ -57,7 +57,7 @@ class brt_render_params(C.Structure):
                 ("aa_mode", C.c_int32), ("tonemap", C.c_int32), ("exposure", C.c_double), ("gamma", C.c_double),
                 ("denoise", C.c_int32), ("_pad0", C.c_int32), ("denoise_strength", C.c_double), ("seed", C.c_uint64),
                 ("direct_lighting", C.c_int32), ("sampler", C.c_int32), ("integrator", C.c_int32), ("accel", C.c_int32),
-                ("spp_batch", C.c_int32), ("count_tests", C.c_int32), ("refill_threshold", C.c_int32), ("paths_in_flight", C.c_int32)]
+                ("spp_batch", C.c_int32), ("count_tests", C.c_int32), ("refill_threshold", C.c_int32), ("paths_in_flight", C.c_int32), ("preview", C.c_int32), ("_pad1", C.c_int32)]
 
 
 class brt_scene_info(C.Structure):

@@ -606,7 +606,18 @@ int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_me
             // progress + cooperative cancel between batches (ray-tracer.js:190,256-261)
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->cancel.load()) return fail(ctx, BRT_E_CANCELLED, "render cancelled");
-            if (cb && s + n < spp) cb((double)(s + n) / spp, user);
+            if (cb && s + n < spp) {
+                if (ctx->rp.preview && p.maxDepth > 0) {
+                    // progressive preview: the sums so far divided by their own sample count (alpha) are a complete image
+                    bool dn = ctx->rp.denoise != 0;
+                    if (dn) CK(ctx->dFloat.ensure(px * 16));
+                    rc = brt_resolve_device(ctx, (const float*)ctx->dAccum.p, (uint8_t*)ctx->dRgba.p, dn ? (float*)ctx->dFloat.p : nullptr, nullptr);
+                    if (rc != BRT_OK) return rc;
+                    CK(cudaMemcpyAsync(rgba8, ctx->dRgba.p, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                }
+                cb((double)(s + n) / spp, user);
+            }
         }
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));

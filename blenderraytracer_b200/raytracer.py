@@ -359,6 +359,7 @@ class RayTracer:
         p.spp_batch, p.count_tests = int(self.sppBatch), 1 if self.countTests else 0
         p.refill_threshold = int(getattr(self, "refillThreshold", 0))
         p.paths_in_flight = int(getattr(self, "pathsInFlight", 0))
+        p.preview = 1 if getattr(self, "preview", False) else 0
         L.check(self._ctx, self._L.brt_set_render_params(self._ctx, C.byref(p)))
         return p
 
@@ -371,7 +372,14 @@ class RayTracer:
         rgba = np.empty((H, W, 4), np.uint8)
         fdat = np.empty((H, W, 4), np.float32) if want_float else None
         lin = np.empty((H, W, 4), np.float32) if want_linear else None
-        cb = L.PROGRESS_CB(lambda f, _u: onProgress(f)) if onProgress else L.PROGRESS_CB()
+        # with self.preview = True, `rgba` already holds the image of the samples traced so far whenever onProgress fires
+        # (pass a two-argument callable to receive it): the reference's progressive canvas blit (ray-tracer.js:236-238)
+        def _cb(f, _u):
+            try:
+                onProgress(f, rgba)
+            except TypeError:
+                onProgress(f)
+        cb = L.PROGRESS_CB(_cb) if onProgress else L.PROGRESS_CB()
         rc = self._L.brt_render(self._ctx, rgba.ctypes.data, fdat.ctypes.data if want_float else None,
                                 lin.ctypes.data if want_linear else None, cb, None)
         L.check(self._ctx, rc)

@@ -132,6 +132,9 @@ typedef struct brt_render_params {
     int32_t count_tests;         /* 1 = counting build of the same traversal (fills brt_stats.tests_*) */
     int32_t refill_threshold;    /* tuning: idle lanes of a warp fetch the next queued ray once this many are idle; 0 = default (8) */
     int32_t paths_in_flight;     /* tuning: samples of a pixel in flight per lane (1..4); 0 = default (2) */
+    int32_t preview;             /* 1 = progressive preview: before every progress callback the image of the samples traced so far
+                                    is resolved into the caller's rgba8 buffer (the reference blits finished rows, ray-tracer.js:236-238) */
+    int32_t _pad1;
 } brt_render_params;
 
 typedef struct brt_scene_info {

@@ -513,6 +513,25 @@ def test_progress_cancel_and_errors(brt, sample_scene):
     assert rt.render().shape == (120, 200, 4)             # and the previous scene is still there
 
 
+def test_progressive_preview(brt, sample_scene):
+    """preview = 1: at every progress callback the caller's buffer holds the image of the samples traced so far, i.e.
+    exactly the render of the first f*spp samples (the reference blits finished rows, ray-tracer.js:236-238; here the whole
+    frame refines)."""
+    W, H, spp = 160, 100, 16
+    rt = brt.RayTracer(W, H, seed=12)
+    assert rt.loadFromJSON(sample_scene)
+    rt.updateRenderSettings(dict(samples=spp, maxBounces=5))
+    rt.sppBatch, rt.preview = 4, True
+    seen = []
+    final = rt.render(onProgress=lambda f, img: seen.append((f, img.copy())))
+    assert [f for f, _ in seen] == [0.25, 0.5, 0.75, 1.0]
+    assert np.array_equal(seen[-1][1], final)
+    rt.preview, rt.sppBatch = False, 0
+    for f, img in seen[:-1]:
+        rt.updateRenderSettings(dict(samples=int(f * spp), maxBounces=5))
+        assert np.array_equal(rt.render(), img), f           # same global sample indices => the same picture
+
+
 def test_direct_lighting_extension_matches_oracle(brt, sample_mesh):
     """EXTENSION (off by default; lights.js is dead code in the reference): point / directional shadow rays.  Pinned only by
     our own oracle's restatement of the same rule."""

@@ -315,15 +315,23 @@ def test_no_cpu_fallback(host, sample_scene):
 
 
 def test_product_never_imports_the_oracle():
-    """The oracle is test infrastructure: nothing under blenderraytracer_b200/ (or its C sources) may reference it."""
+    """The oracle is test infrastructure: nothing under blenderraytracer_b200/ (Python or C/CUDA sources) may import, link,
+    load or call it, and libbrt.so must not depend on liboracle.so."""
+    import subprocess
     pkg = os.path.join(ROOT, "blenderraytracer_b200")
+    needles = ("liboracle", "import oracle", "from oracle", "oracle/", "oracle.oracle", "orc_", "brt_oracle")
     for dirpath, _, files in os.walk(pkg):
-        if os.path.basename(dirpath) == "build":
+        if os.path.basename(dirpath) in ("build", "__pycache__"):
             continue
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="replace").read()
-                assert "oracle" not in text.lower() or f in ("brt_device.cuh",) and "liboracle" not in text, os.path.join(dirpath, f)
+                for n in needles:
+                    assert n not in text, f"{os.path.join(dirpath, f)} references the oracle ({n})"
+    deps = subprocess.check_output(["ldd", L.LIB_PATH], text=True)
+    assert "oracle" not in deps
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", L.LIB_PATH], text=True)
+    assert "orc_" not in syms
 
 
 def test_scene_generators_are_deterministic():
