@@ -6,8 +6,10 @@ does not touch the GPU; constructing a ``RayTracer`` does, and fails loudly with
 """
 from ._lib import BrtError, LIB_PATH, load  # noqa: F401
 from .raytracer import RayTracer, make_perm  # noqa: F401
-from .scene import (Box, Dielectric, DirectionalLight, Emissive, Lambertian, Metal, Plane, PointLight, Sphere,  # noqa: F401
-                    Triangle, TriangleMesh, World)
+from .scene import (Box, CheckerTexture, Dielectric, DirectionalLight, Emissive, Lambertian, MarbleTexture, Metal,  # noqa: F401
+                    NoiseTexture, Plane, PointLight, SolidColor, Sphere, TexturedLambertian, TexturedMetal, Triangle,
+                    TriangleMesh, WoodTexture, World)
 
 __all__ = ["RayTracer", "World", "Sphere", "Plane", "Box", "Triangle", "TriangleMesh", "Lambertian", "Metal", "Dielectric",
-           "Emissive", "PointLight", "DirectionalLight", "BrtError", "make_perm", "load", "LIB_PATH"]
+           "Emissive", "PointLight", "DirectionalLight", "SolidColor", "CheckerTexture", "NoiseTexture", "MarbleTexture", "WoodTexture",
+           "TexturedLambertian", "TexturedMetal", "BrtError", "make_perm", "load", "LIB_PATH"]

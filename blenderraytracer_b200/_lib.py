@@ -25,7 +25,14 @@ d3 = C.c_double * 3
 
 
 class brt_material(C.Structure):
-    _fields_ = [("type", C.c_int32), ("_pad", C.c_int32), ("color", d3), ("param", C.c_double)]
+    _fields_ = [("type", C.c_int32), ("texture", C.c_int32), ("color", d3), ("param", C.c_double)]
+
+
+TEX = {"solid": 0, "checker": 1, "noise": 2, "marble": 3, "wood": 4}
+
+
+class brt_texture(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("odd", d3), ("even", d3), ("scale", C.c_double), ("perm", C.c_uint8 * 256)]
 
 
 class brt_object(C.Structure):
@@ -41,7 +48,8 @@ class brt_scene_desc(C.Structure):
     _fields_ = [("objects", C.POINTER(brt_object)), ("n_objects", C.c_int32), ("_pad0", C.c_int32),
                 ("materials", C.POINTER(brt_material)), ("n_materials", C.c_int32), ("_pad1", C.c_int32),
                 ("mesh_triangles", C.POINTER(C.c_double)), ("n_mesh_triangles", C.c_int64),
-                ("lights", C.POINTER(brt_light)), ("n_lights", C.c_int32), ("_pad2", C.c_int32)]
+                ("lights", C.POINTER(brt_light)), ("n_lights", C.c_int32), ("_pad2", C.c_int32),
+                ("textures", C.POINTER(brt_texture)), ("n_textures", C.c_int32), ("_pad3", C.c_int32)]
 
 
 class brt_camera(C.Structure):
@@ -112,6 +120,7 @@ SIGNATURES = {
     "brt_eval_background": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_float)]),
     "brt_debug_rng_stream": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]),
     "brt_postprocess_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "brt_eval_texture": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_float)]),
     "brt_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 

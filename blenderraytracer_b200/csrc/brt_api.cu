@@ -35,7 +35,7 @@ struct brt_ctx {
     brt_camera cam{}; bool haveCam = false;
     brt_render_params rp{};
     // device scene
-    DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm, dPrim64;
+    DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm, dPrim64, dTex, dTexPerm;
     float4* dNodes = nullptr;
     DevScene dev{};
     bool sceneDirty = true, permDirty = true;
@@ -105,7 +105,7 @@ void brt_destroy(brt_ctx* ctx) {
     if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->dSph, &ctx->dPln, &ctx->dBox, &ctx->dTri, &ctx->dMeta, &ctx->dMat, &ctx->dMatType, &ctx->dLights, &ctx->dPerm, &ctx->dPrim64,
+    DevBuf* bufs[] = { &ctx->dSph, &ctx->dPln, &ctx->dBox, &ctx->dTri, &ctx->dMeta, &ctx->dMat, &ctx->dMatType, &ctx->dLights, &ctx->dPerm, &ctx->dPrim64, &ctx->dTex, &ctx->dTexPerm,
                        &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch, &ctx->dPlanes,
                        &ctx->dObj64, &ctx->dTris64 };
     for (DevBuf* b : bufs) b->release();
@@ -144,7 +144,11 @@ static int validate_scene(brt_ctx* ctx, const HostScene& s) {
                 return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": mesh triangle range out of bounds");
         }
     }
-    for (const brt_material& m : s.materials) if (m.type < 0 || m.type > 3) return fail(ctx, BRT_E_INVALID, "bad material type");
+    for (const brt_material& m : s.materials) {
+        if (m.type < 0 || m.type > 3) return fail(ctx, BRT_E_INVALID, "bad material type");
+        if (m.texture < 0 || (size_t)m.texture > s.textures.size()) return fail(ctx, BRT_E_INVALID, "bad texture index");
+    }
+    for (const brt_texture& t : s.textures) if (t.kind < BRT_TEX_SOLID || t.kind > BRT_TEX_WOOD) return fail(ctx, BRT_E_INVALID, "bad texture kind");
     for (const brt_light& l : s.lights) if (l.type < 0 || l.type > 1) return fail(ctx, BRT_E_INVALID, "bad light type");
     return BRT_OK;
 }
@@ -168,13 +172,15 @@ int brt_scene_load_json(brt_ctx* ctx, const char* utf8, size_t len, int fw, int 
 
 int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {
     if (!ctx || !d) return BRT_E_INVALID;
-    if (d->n_objects < 0 || d->n_materials < 0 || d->n_lights < 0 || d->n_mesh_triangles < 0) return fail(ctx, BRT_E_INVALID, "negative count");
+    if (d->n_objects < 0 || d->n_materials < 0 || d->n_lights < 0 || d->n_mesh_triangles < 0 || d->n_textures < 0) return fail(ctx, BRT_E_INVALID, "negative count");
+    if (d->n_textures && !d->textures) return fail(ctx, BRT_E_INVALID, "null array with non-zero count");
     if ((d->n_objects && !d->objects) || (d->n_materials && !d->materials) || (d->n_lights && !d->lights) || (d->n_mesh_triangles && !d->mesh_triangles))
         return fail(ctx, BRT_E_INVALID, "null array with non-zero count");
     HostScene sc;
     sc.objects.assign(d->objects, d->objects + d->n_objects);
     sc.materials.assign(d->materials, d->materials + d->n_materials);
     sc.lights.assign(d->lights, d->lights + d->n_lights);
+    if (d->n_textures) sc.textures.assign(d->textures, d->textures + d->n_textures);
     sc.meshTris.assign(d->mesh_triangles, d->mesh_triangles + 9 * (size_t)d->n_mesh_triangles);
     for (brt_object& o : sc.objects) if (o.type == BRT_OBJ_PLANE) {               // geometry.js:52
         double l = std::sqrt(o.b[0] * o.b[0] + o.b[1] * o.b[1] + o.b[2] * o.b[2]);
@@ -235,7 +241,14 @@ static int upload_scene(brt_ctx* ctx) {
             }
         }
     }
-    for (const brt_material& m : s.materials) { mat.push_back(f4(m.color[0], m.color[1], m.color[2], m.param)); matType.push_back(m.type); }
+    // material type in the low byte, 1-based texture index above it (TexturedLambertian / TexturedMetal)
+    for (const brt_material& m : s.materials) { mat.push_back(f4(m.color[0], m.color[1], m.color[2], m.param)); matType.push_back(m.type | (m.texture << 8)); }
+    std::vector<float4> tex; std::vector<unsigned char> texPerm;
+    for (const brt_texture& t : s.textures) {
+        tex.push_back(f4(t.odd[0], t.odd[1], t.odd[2], (double)t.kind));
+        tex.push_back(f4(t.even[0], t.even[1], t.even[2], t.scale));
+        for (int k = 0; k < 512; k++) texPerm.push_back(t.perm[k & 255]);      // doubled table (noise.js:16-17)
+    }
     for (const brt_light& l : s.lights) {
         lights.push_back(f4(l.v[0], l.v[1], l.v[2], l.type == BRT_LIGHT_DIRECTIONAL ? 1.0 : 0.0));
         lights.push_back(f4(l.color[0] * l.intensity, l.color[1] * l.intensity, l.color[2] * l.intensity, 0));
@@ -267,10 +280,13 @@ static int upload_scene(brt_ctx* ctx) {
     CK(up(ctx->dMatType, matType.data(), matType.size() * sizeof(int)));
     CK(up(ctx->dLights, lights.data(), lights.size() * sizeof(float4)));
     CK(up(ctx->dPrim64, prim64.data(), prim64.size() * sizeof(double)));
+    CK(up(ctx->dTex, tex.data(), tex.size() * sizeof(float4)));
+    CK(up(ctx->dTexPerm, texPerm.data(), texPerm.size()));
     CK(cudaStreamSynchronize(ctx->stream));
     d.sph = (const float4*)ctx->dSph.p; d.pln = (const float4*)ctx->dPln.p; d.box = (const float4*)ctx->dBox.p; d.tri = (const float4*)ctx->dTri.p;
     d.meta = (const int4*)ctx->dMeta.p; d.mat = (const float4*)ctx->dMat.p; d.matType = (const int*)ctx->dMatType.p;
     d.lights = (const float4*)ctx->dLights.p; d.prim64 = (const double*)ctx->dPrim64.p;
+    d.tex = (const float4*)ctx->dTex.p; d.texPerm = (const unsigned char*)ctx->dTexPerm.p; d.nTex = (int)s.textures.size();
     auto t1 = std::chrono::steady_clock::now();
     // LBVH over the bounded primitives
     if (ctx->dNodes) { cudaFree(ctx->dNodes); ctx->dNodes = nullptr; }
@@ -334,6 +350,7 @@ int brt_scene_get_flat(brt_ctx* ctx, brt_scene_desc* out) {
     out->materials = s.materials.data(); out->n_materials = (int)s.materials.size();
     out->mesh_triangles = s.meshTris.data(); out->n_mesh_triangles = (int64_t)(s.meshTris.size() / 9);
     out->lights = s.lights.data(); out->n_lights = (int)s.lights.size();
+    out->textures = s.textures.data(); out->n_textures = (int)s.textures.size();
     return BRT_OK;
 }
 
@@ -742,6 +759,26 @@ int brt_eval_background(brt_ctx* ctx, const double* dirs, int n, float* out_rgb)
     sc.bgKind = ctx->bg.kind; sc.bgR = (float)ctx->bg.color[0]; sc.bgG = (float)ctx->bg.color[1]; sc.bgB = (float)ctx->bg.color[2];
     sc.skyIntensity = (float)ctx->bg.intensity;
     CK(launch_eval_background(sc, dIn, n, dOut, ctx->stream));
+    CK(cudaMemcpyAsync(out_rgb, dOut, f.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRT_OK;
+}
+
+int brt_eval_texture(brt_ctx* ctx, int tex_index, const double* points, int n, float* out_rgb) {
+    if (!ctx || !points || !out_rgb || n < 0) return BRT_E_INVALID;
+    NEED_GPU();
+    if (!ctx->haveScene) return fail(ctx, BRT_E_NOSCENE, "no scene loaded");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_scene(ctx);
+    if (rc != BRT_OK) return rc;
+    if (tex_index < 0 || tex_index >= ctx->dev.nTex) return fail(ctx, BRT_E_INVALID, "texture index out of range");
+    if (n == 0) return BRT_OK;
+    std::vector<float> f(3 * (size_t)n);
+    for (size_t i = 0; i < f.size(); i++) f[i] = (float)points[i];
+    CK(ctx->dScratch.ensure(f.size() * 8));
+    float* dIn = (float*)ctx->dScratch.p; float* dOut = dIn + f.size();
+    CK(cudaMemcpyAsync(dIn, f.data(), f.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_eval_texture(ctx->dev, tex_index, dIn, n, dOut, ctx->stream));
     CK(cudaMemcpyAsync(out_rgb, dOut, f.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return BRT_OK;

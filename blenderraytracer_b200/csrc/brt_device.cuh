@@ -32,11 +32,13 @@ struct DevScene {
     const float4* nodes; // 4 x float4 per BVH node (see bvh.cu)
     const float4* lights;// 2 per light: (v.xyz, type), (color*intensity .xyz, 0)
     const unsigned char* perm;  // 512-entry doubled Perlin permutation      noise.js:7-17
+    const float4* tex;    // 2 per texture: (odd.rgb, kind), (even.rgb, scale)        textures.js
+    const unsigned char* texPerm;   // 512 per texture: its own doubled Perlin table     textures.js:44,58,74
     const double* prim64; // 9 doubles per primitive (unified index, as meta): float64 copy used ONLY to evaluate the
                           // primitive a PRIMARY ray's fp32 traversal selected (t / P / N within 1e-5 of the float64 reference)
     int nSph, nPln, nBox, nTri;
     int baseSph, basePln, baseBox, baseTri;   // offsets into meta
-    int nNodes, nLights;
+    int nNodes, nLights, nTex;
     int bgKind;
     float bgR, bgG, bgB, skyIntensity;
     int bvhStackDepth;
@@ -229,7 +231,7 @@ __device__ __forceinline__ void consider(const DevScene& sc, Hit& best, float t,
         // any-hit for the direct-lighting extension: strictly closer than the light, emissive primitives ignored
         if (t < best.t) {
             int4 m = __ldg(&sc.meta[meta_index(sc, pid)]);
-            if (__ldg(&sc.matType[m.y]) != 3) { best.t = t; best.pid = pid; }
+            if ((__ldg(&sc.matType[m.y]) & 255) != 3) { best.t = t; best.pid = pid; }
         }
         return;
     }
@@ -550,6 +552,47 @@ __device__ inline float3 background(const DevScene& sc, float3 D) {
         // (1-t)*(1,1,1) + t*(0.5,0.7,1.0)
         return f3(__fmul_rn(fmaf(t, 0.5f, __fsub_rn(1.0f, t)), I), __fmul_rn(fmaf(t, 0.7f, __fsub_rn(1.0f, t)), I), __fmul_rn(fmaf(t, 1.0f, __fsub_rn(1.0f, t)), I));
     }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- surface textures (textures.js)
+// value(u, v, p) of every reference texture depends on the hit point only.
+__device__ inline float3 texture_value(const DevScene& sc, int ti, float3 P) {
+    float4 a = ldg4(sc.tex + 2 * ti), b = ldg4(sc.tex + 2 * ti + 1);
+    const int kind = (int)a.w;
+    const float scale = b.w;
+    const unsigned char* perm = sc.texPerm + 512 * ti;
+    switch (kind) {
+    case 1: {                                                                                                        // :33-36
+        float sines = __fmul_rn(__fmul_rn(sinf(__fmul_rn(scale, P.x)), sinf(__fmul_rn(scale, P.y))), sinf(__fmul_rn(scale, P.z)));
+        return sines < 0.f ? f3(a.x, a.y, a.z) : f3(b.x, b.y, b.z);
+    }
+    case 2: {                                                                                                        // :47-50
+        float n = perlin_noise(perm, __fmul_rn(P.x, scale), __fmul_rn(P.y, scale), __fmul_rn(P.z, scale));
+        float v = __fmul_rn(0.5f, __fadd_rn(1.f, n));
+        return f3(v, v, v);
+    }
+    case 3: {                                                                                                        // :61-65, noise.js:63-75
+        float accum = 0.f, weight = 1.f;
+        float3 q = P * scale;
+        for (int i = 0; i < 7; i++) {
+            accum = fmaf(weight, perlin_noise(perm, q.x, q.y, q.z), accum);
+            weight = __fmul_rn(weight, 0.5f);
+            q = q * 2.f;
+        }
+        float m = __fmul_rn(0.5f, __fadd_rn(1.f, sinf(fmaf(10.f, fabsf(accum), __fmul_rn(scale, P.z)))));
+        float w = __fsub_rn(1.f, m);
+        return f3(fmaf(0.6f, w, __fmul_rn(0.9f, m)), fmaf(0.4f, w, __fmul_rn(0.8f, m)), fmaf(0.3f, w, __fmul_rn(0.7f, m)));
+    }
+    case 4: {                                                                                                        // :77-82
+        float s20 = __fmul_rn(scale, 20.f);
+        float grain = perlin_noise(perm, __fmul_rn(P.x, s20), __fmul_rn(P.y, s20), __fmul_rn(P.z, s20));
+        float rings = sinf(fmaf(grain, 10.f, __fmul_rn(scale, sqrtf(fmaf(P.x, P.x, __fmul_rn(P.z, P.z))))));
+        float m = __fmul_rn(0.5f, __fadd_rn(1.f, rings));
+        float w = __fsub_rn(1.f, m);
+        return f3(fmaf(0.4f, w, __fmul_rn(0.8f, m)), fmaf(0.2f, w, __fmul_rn(0.5f, m)), fmaf(0.1f, w, __fmul_rn(0.2f, m)));
+    }
+    default: return f3(a.x, a.y, a.z);                                                                               // :21
     }
 }
 

@@ -11,6 +11,7 @@ struct HostScene {                       // World (reference js/world.js:9-18)
     std::vector<brt_object> objects;     // world.objects, in order: index = object ID
     std::vector<brt_material> materials;
     std::vector<brt_light> lights;       // world.lights
+    std::vector<brt_texture> textures;   // textures.js instances referenced by brt_material.texture (1-based)
     std::vector<double> meshTris;        // 9 doubles per mesh triangle
 };
 

@@ -36,6 +36,7 @@ cudaError_t launch_sum_planes(float4* accum, const float4* planes, int nPlanes, 
 cudaError_t launch_primary_aov(const PTParams& p, bool useBvh, int* objId, int* triId, float* t, float* nrm, unsigned char* front,
                                cudaStream_t st);
 cudaError_t launch_eval_background(const DevScene& sc, const float* dirs, int n, float* out, cudaStream_t st);
+cudaError_t launch_eval_texture(const DevScene& sc, int texIndex, const float* points, int n, float* out, cudaStream_t st);
 cudaError_t launch_rng_stream(uint32_t lo, uint32_t hi, uint32_t pixel, uint32_t sample, int n, float* out, cudaStream_t st);
 cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st);
 

@@ -77,8 +77,9 @@ __device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t p
 // ------------------------------------------------------------------------------------------- materials (materials.js)
 // Returns false when the path ends here (emissive, absorbed metal).  `att` multiplies the throughput.
 template <int SAMPLER>
-__device__ __forceinline__ bool scatter(const PTParams& p, int matType, float4 m, const Surface& sf, float3 Din, uint32_t pix,
+__device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m, const Surface& sf, float3 Din, uint32_t pix,
                                         uint32_t s, int bounce, RngSeq& rng, float3& Dout, float3& att) {
+    const int matType = matWord & 255, tex = matWord >> 8;           // 1-based texture index above the type (materials.js:99-126)
     float u0 = 0.f, u1 = 0.f, u2 = 0.f;
     if (SAMPLER == 0) {
         uint4 r = philox4x32_10(pix, s, (uint32_t)(bounce + 1), PHILOX_TAG, p.seedLo, p.seedHi);
@@ -93,7 +94,7 @@ __device__ __forceinline__ bool scatter(const PTParams& p, int matType, float4 m
             unit = normalize0(q);
         }
         Dout = sf.N + unit;
-        att = f3(m.x, m.y, m.z);
+        att = tex ? texture_value(p.sc, tex - 1, sf.P) : f3(m.x, m.y, m.z);
         return true;
     }
     if (matType == 1) {                                                       // Metal (materials.js:36-41)
@@ -102,7 +103,7 @@ __device__ __forceinline__ bool scatter(const PTParams& p, int matType, float4 m
         if (SAMPLER == 0) ball = uniform_sphere(u0, u1) * cbrtf(u2);
         else { do { ball = f3(rng.next() * 2.f - 1.f, rng.next() * 2.f - 1.f, rng.next() * 2.f - 1.f); } while (dot(ball, ball) >= 1.0f); }
         Dout = madd(ball, m.w, refl);
-        att = f3(m.x, m.y, m.z);
+        att = tex ? texture_value(p.sc, tex - 1, sf.P) : f3(m.x, m.y, m.z);
         return dot(Dout, sf.N) > 0.f;
     }
     if (matType == 2) {                                                       // Dielectric (materials.js:51-83)
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
     extern __shared__ uint32_t smem[];
     constexpr int NS = 32 * K;                                        // path slots per warp
     constexpr int NW = slot_words(SAMPLER);
+    constexpr bool PRECISE = SAMPLER == 1;                            // see k_pathtrace_mega
     constexpr int WARP_WORDS = NW * NS + 32 * SMEM_STACK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
                     sum = sum + beta * background(sc, D);
                 } else {
                     Surface sf = make_surface(sc, best, O, D, self);
-                    if (depth == 0) {                                         // primary hit: float64 evaluation of the selected primitive
+                    if (PRECISE && depth == 0) {                              // primary hit: float64 evaluation of the selected primitive
                         D3 O64, D64; double t64;
                         RngSeq again;                                         // re-derive this path's camera sample (cheaper than 4 words per slot)
                         CamSample cam = camera_sample<SAMPLER>(p, pix, cs, again);
@@ -208,8 +210,8 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
                     }
                     float4 m = ldg4(sc.mat + sf.matId);
                     int mt = __ldg(sc.matType + sf.matId);
-                    if (mt == 3) sum = sum + beta * (f3(m.x, m.y, m.z) * m.w);    // emitted (materials.js:95)
-                    if (DIRECT && mt == 0) {
+                    if ((mt & 255) == 3) sum = sum + beta * (f3(m.x, m.y, m.z) * m.w);    // emitted (materials.js:95)
+                    if (DIRECT && (mt & 255) == 0) {
                         // EXTENSION (off by default): lights.js:22-47 give direction / colour / distance.
                         for (int li = 0; li < sc.nLights; li++) {
                             float4 l0 = ldg4(sc.lights + 2 * li), l1 = ldg4(sc.lights + 2 * li + 1);
@@ -248,9 +250,12 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
                 if (s < sEnd) {
                     cs = (uint32_t)s++;
                     CamSample cam = camera_sample<SAMPLER>(p, pix, cs, rng);
-                    D3 O64, D64;
-                    camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
-                    float3 O = tof3(O64), D = tof3(D64);
+                    float3 O, D;
+                    if (PRECISE) {
+                        D3 O64, D64;
+                        camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
+                        O = tof3(O64); D = tof3(D64);
+                    } else camera_ray32(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                     SLOT_F(F_OX, slot) = O.x; SLOT_F(F_OY, slot) = O.y; SLOT_F(F_OZ, slot) = O.z;
                     SLOT_F(F_DX, slot) = D.x; SLOT_F(F_DY, slot) = D.y; SLOT_F(F_DZ, slot) = D.z;
                     SLOT_F(F_BX, slot) = 1.f; SLOT_F(F_BY, slot) = 1.f; SLOT_F(F_BZ, slot) = 1.f;
@@ -419,8 +424,8 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
             }
             float4 m = ldg4(sc.mat + sf.matId);
             int mt = __ldg(sc.matType + sf.matId);
-            if (mt == 3) sum = sum + beta * (f3(m.x, m.y, m.z) * m.w);        // emitted (materials.js:95)
-            if (DIRECT && mt == 0) {
+            if ((mt & 255) == 3) sum = sum + beta * (f3(m.x, m.y, m.z) * m.w);        // emitted (materials.js:95)
+            if (DIRECT && (mt & 255) == 0) {
                 // EXTENSION (off by default): lights.js:22-47 give direction / colour / distance.
                 for (int li = 0; li < sc.nLights; li++) {
                     float4 l0 = ldg4(sc.lights + 2 * li), l1 = ldg4(sc.lights + 2 * li + 1);
@@ -495,6 +500,13 @@ __global__ void k_eval_background(DevScene sc, const float* dirs, int n, float* 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float3 c = background(sc, f3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+    out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
+__global__ void k_eval_texture(DevScene sc, int ti, const float* pts, int n, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 c = texture_value(sc, ti, f3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
     out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
 }
 
@@ -581,6 +593,10 @@ cudaError_t launch_primary_aov(const PTParams& p, bool useBvh, int* objId, int* 
 
 cudaError_t launch_eval_background(const DevScene& sc, const float* dirs, int n, float* out, cudaStream_t st) {
     k_eval_background<<<(n + 127) / 128, 128, 0, st>>>(sc, dirs, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_eval_texture(const DevScene& sc, int texIndex, const float* points, int n, float* out, cudaStream_t st) {
+    k_eval_texture<<<(n + 127) / 128, 128, 0, st>>>(sc, texIndex, points, n, out);
     return cudaGetLastError();
 }
 cudaError_t launch_rng_stream(uint32_t lo, uint32_t hi, uint32_t pixel, uint32_t sample, int n, float* out, cudaStream_t st) {

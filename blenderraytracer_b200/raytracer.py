@@ -425,7 +425,11 @@ class RayTracer:
         out.materials, out.n_materials = mats, d.n_materials
         out.lights, out.n_lights = lights, d.n_lights
         out.mesh_triangles, out.n_mesh_triangles = tris.ctypes.data_as(C.POINTER(C.c_double)), n
-        return out, (objs, mats, lights, tris)
+        texs = (L.brt_texture * max(1, d.n_textures))()
+        if d.n_textures:
+            C.memmove(texs, d.textures, C.sizeof(L.brt_texture) * d.n_textures)
+        out.textures, out.n_textures = texs, d.n_textures
+        return out, (objs, mats, lights, tris, texs)
 
     def setSceneFlat(self, desc_keep):
         """brt_scene_set_flat with a (desc, keepalive) pair from sceneFlatDesc() / World.flatten()."""
@@ -452,6 +456,14 @@ class RayTracer:
         out = np.empty((d.shape[0], 3), np.float32)
         L.check(self._ctx, self._L.brt_eval_background(self._ctx, d.ctypes.data_as(C.POINTER(C.c_double)), d.shape[0],
                                                        out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def evalTexture(self, tex_index, points) -> np.ndarray:
+        """textures[tex_index].value(u, v, p) (js/textures.js) for an array of points, evaluated by the device code."""
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 3))
+        out = np.empty((pts.shape[0], 3), np.float32)
+        L.check(self._ctx, self._L.brt_eval_texture(self._ctx, int(tex_index), pts.ctypes.data_as(C.POINTER(C.c_double)), pts.shape[0],
+                                                    out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
     def postprocess(self, linear_mean) -> np.ndarray:

@@ -56,6 +56,66 @@ class Emissive:
         return L.MAT_EMISSIVE, _v(self.color), float(self.intensity)
 
 
+# ---- textures (js/textures.js) and textured materials (js/materials.js:99-126) --------------------------------
+@dataclass
+class SolidColor:
+    color: Sequence[float]
+
+    def _tex(self):
+        return L.TEX["solid"], _v(self.color), (0.0, 0.0, 0.0), 1.0, None
+
+
+@dataclass
+class CheckerTexture:
+    odd: Sequence[float]
+    even: Sequence[float]
+    scale: float = 10
+
+    def _tex(self):
+        return L.TEX["checker"], _v(self.odd), _v(self.even), float(self.scale), None
+
+
+class _NoiseBased:
+    """`perm256`: the texture's own PerlinNoise table (textures.js:44,58,74 draw it with Math.random; an input here)."""
+    kind = "noise"
+
+    def __init__(self, scale=1, perm256=None):
+        self.scale = float(scale)
+        self.perm = np.arange(256, dtype=np.uint8) if perm256 is None else np.asarray(perm256, dtype=np.uint8).reshape(256)
+
+    def _tex(self):
+        return L.TEX[self.kind], (1.0, 1.0, 1.0), (1.0, 1.0, 1.0), self.scale, self.perm
+
+
+class NoiseTexture(_NoiseBased):
+    kind = "noise"
+
+
+class MarbleTexture(_NoiseBased):
+    kind = "marble"
+
+
+class WoodTexture(_NoiseBased):
+    kind = "wood"
+
+
+@dataclass
+class TexturedLambertian:
+    texture: object
+
+    def _desc(self):
+        return L.MAT_LAMBERTIAN, (1.0, 1.0, 1.0), 0.0
+
+
+@dataclass
+class TexturedMetal:
+    texture: object
+    roughness: float = 0.0
+
+    def _desc(self):
+        return L.MAT_METAL, (1.0, 1.0, 1.0), float(self.roughness)
+
+
 # ---- geometry (js/geometry.js) ----------------------------------------------------------------------------
 @dataclass
 class Sphere:
@@ -140,9 +200,20 @@ class World:
         mats = (L.brt_material * max(n, 1))()
         meshes = []
         first = 0
+        texs = [o.material.texture for o in self.objects if hasattr(o.material, "texture")]
+        textures = (L.brt_texture * max(len(texs), 1))()
+        n_tex = 0
         for i, o in enumerate(self.objects):
             t, col, p = o.material._desc()
             mats[i].type, mats[i].color, mats[i].param = t, L.d3(*col), p
+            if hasattr(o.material, "texture"):
+                kind, odd, even, scale, perm = o.material.texture._tex()
+                tx = textures[n_tex]
+                tx.kind, tx.odd, tx.even, tx.scale = kind, L.d3(*odd), L.d3(*even), scale
+                if perm is not None:
+                    C.memmove(tx.perm, np.ascontiguousarray(perm).ctypes.data, 256)
+                n_tex += 1
+                mats[i].texture = n_tex                      # 1-based
             ob = objs[i]
             ob.material = i
             if isinstance(o, Sphere):
@@ -176,4 +247,5 @@ class World:
         d.mesh_triangles = tris.ctypes.data_as(C.POINTER(C.c_double))
         d.n_mesh_triangles = tris.shape[0]
         d.lights, d.n_lights = lights, nl
-        return d, (objs, mats, tris, lights)
+        d.textures, d.n_textures = textures, n_tex
+        return d, (objs, mats, tris, lights, textures)

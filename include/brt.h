@@ -49,6 +49,7 @@ enum {
 /* ---- enumerations (values are ABI) ---------------------------------------------------------------- */
 enum { BRT_OBJ_SPHERE = 0, BRT_OBJ_PLANE = 1, BRT_OBJ_BOX = 2, BRT_OBJ_TRIANGLE = 3, BRT_OBJ_MESH = 4 };     /* js/geometry.js */
 enum { BRT_MAT_LAMBERTIAN = 0, BRT_MAT_METAL = 1, BRT_MAT_DIELECTRIC = 2, BRT_MAT_EMISSIVE = 3 };            /* js/materials.js */
+enum { BRT_TEX_SOLID = 0, BRT_TEX_CHECKER = 1, BRT_TEX_NOISE = 2, BRT_TEX_MARBLE = 3, BRT_TEX_WOOD = 4 };       /* js/textures.js */
 enum { BRT_LIGHT_POINT = 0, BRT_LIGHT_DIRECTIONAL = 1 };                                                    /* js/lights.js */
 enum { BRT_BG_GRADIENT = 0, BRT_BG_SOLID = 1, BRT_BG_HDRI = 2, BRT_BG_PROCEDURAL_SKY = 3 };                 /* js/world.js:35-110 */
 /* CENTER = any other antiAliasing string: pixel-centre samples, but still `samples` of them (ray-tracer.js:142-148 with :201) */
@@ -68,10 +69,24 @@ enum { BRT_ACCEL_AUTO = 0, BRT_ACCEL_BRUTE = 1, BRT_ACCEL_BVH = 2 };
 /* ---- scene descriptors ----------------------------------------------------------------------------- */
 typedef struct brt_material {
     int32_t type;        /* BRT_MAT_* */
-    int32_t _pad;
+    int32_t texture;     /* 0 = none; k > 0 = brt_scene_desc.textures[k-1]: TexturedLambertian / TexturedMetal (materials.js:99-126),
+                            attenuation = texture.value(u, v, point) instead of `color` (lambertian / metal only) */
     double color[3];     /* albedo (lambertian/metal) or emissive colour; ignored for dielectric */
     double param;        /* metal: roughness (clamped min(r,1), materials.js:33) | dielectric: ior | emissive: intensity */
 } brt_material;
+
+/* js/textures.js:9-82.  Every value(u, v, p) there uses only the hit point p.  The reference never instantiates these
+ * (createTexture has no caller, ray-tracer.js:79-100) and its scene JSON has no texture fields, so textures reach the
+ * engine only through brt_scene_set_flat.  Each noise-based texture owns a PerlinNoise with a random permutation
+ * (textures.js:44,58,74): `perm` is that table (first 256 entries of PerlinNoise.p). */
+typedef struct brt_texture {
+    int32_t kind;        /* BRT_TEX_* */
+    int32_t _pad;
+    double odd[3];       /* checker: odd colour | solid: the colour */
+    double even[3];      /* checker: even colour */
+    double scale;        /* checker / noise / marble / wood scale */
+    uint8_t perm[256];
+} brt_texture;
 
 /* One entry per element of world.objects, IN ORDER — the index is the "object ID" (world.js:24-30). */
 typedef struct brt_object {
@@ -98,6 +113,7 @@ typedef struct brt_scene_desc {
     const double* mesh_triangles;   /* 9 doubles per triangle: v0.xyz v1.xyz v2.xyz */
     int64_t n_mesh_triangles;
     const brt_light* lights;        int32_t n_lights;      int32_t _pad2;
+    const brt_texture* textures;    int32_t n_textures;    int32_t _pad3;   /* may be NULL / 0 */
 } brt_scene_desc;
 
 /* js/camera.js.  Either the constructor arguments (camera.js:8) or, with use_derived = 1, the derived
@@ -247,6 +263,8 @@ int brt_eval_background(brt_ctx* ctx, const double* dirs, int n, float* out_rgb)
 int brt_debug_rng_stream(brt_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, int n, float* out);
 /* Run only the post-processing kernels on a HOST linear-mean image (W*H*4 fp32) with the ctx render params. */
 int brt_postprocess_host(brt_ctx* ctx, const float* linear_mean, uint8_t* rgba8, float* float_data);
+/* textures[tex_index].value(u, v, p) for n points (HOST in: n*3 doubles; HOST out: n*3 floats), evaluated by the device code. */
+int brt_eval_texture(brt_ctx* ctx, int tex_index, const double* points, int n, float* out_rgb);
 /* Dense FFMA micro-benchmark on this device: the measured FP32 roofline denominator (TFLOP/s). */
 int brt_measure_fp32_peak(brt_ctx* ctx, double* tflops);
 

@@ -90,14 +90,20 @@ static napi_value js_load_scene_json(napi_env env, napi_callback_info info) {
 }
 
 /* setSceneFlat(ctx, objects Float64Array[13 n], materials Float64Array[5 m], meshTris Float64Array[9 t], lights Float64Array[8 l])
- * objects: type, material, a.xyz, b.xyz, c.xyz, firstTri, triCount — one row per world.objects entry, in order (world.js:24-30) */
+ * objects: type, material, a.xyz, b.xyz, c.xyz, firstTri, triCount — one row per world.objects entry, in order (world.js:24-30)
+ * materials: type, r, g, b, param, texture(1-based, 0 = none) — 6 per material
+ * optional: textures Float64Array[8 k] (kind, odd.rgb, even.rgb, scale) + texturePerms Uint8Array[256 k]   (js/textures.js) */
 static napi_value js_set_scene_flat(napi_env env, napi_callback_info info) {
-    ARGS(5);
+    ARGS(7);
     brt_ctx* ctx = get_ctx(env, argv[0]);
     size_t no, nm, nt, nl;
     double* o = f64_array(env, argv[1], &no); double* m = f64_array(env, argv[2], &nm);
     double* t = f64_array(env, argv[3], &nt); double* l = f64_array(env, argv[4], &nl);
-    no /= 13; nm /= 5; nt /= 9; nl /= 8;
+    no /= 13; nm /= 6; nt /= 9; nl /= 8;
+    size_t nx = 0; double* x = argc >= 6 ? f64_array(env, argv[5], &nx) : NULL; nx /= 8;
+    const uint8_t* xp = NULL;
+    if (argc >= 7) { napi_typedarray_type ty; void* data = NULL; size_t len = 0;
+        if (napi_get_typedarray_info(env, argv[6], &ty, &len, &data, NULL, NULL) == napi_ok && ty == napi_uint8_array && len >= 256 * nx) xp = (const uint8_t*)data; }
     brt_object* objs = (brt_object*)calloc(no ? no : 1, sizeof(brt_object));
     brt_material* mats = (brt_material*)calloc(nm ? nm : 1, sizeof(brt_material));
     brt_light* lights = (brt_light*)calloc(nl ? nl : 1, sizeof(brt_light));
@@ -108,13 +114,20 @@ static napi_value js_set_scene_flat(napi_env env, napi_callback_info info) {
         memcpy(objs[i].a, r + 2, 24); memcpy(objs[i].b, r + 5, 24); memcpy(objs[i].c, r + 8, 24);
         objs[i].first_tri = (int64_t)r[11]; objs[i].tri_count = (int64_t)r[12];
     }
-    for (size_t i = 0; i < nm; i++) { const double* r = m + 5 * i; mats[i].type = (int32_t)r[0]; memcpy(mats[i].color, r + 1, 24); mats[i].param = r[4]; }
+    for (size_t i = 0; i < nm; i++) { const double* r = m + 6 * i; mats[i].type = (int32_t)r[0]; memcpy(mats[i].color, r + 1, 24); mats[i].param = r[4]; mats[i].texture = (int32_t)r[5]; }
+    brt_texture* texs = (brt_texture*)calloc(nx ? nx : 1, sizeof(brt_texture));
+    if (!texs) { free(objs); free(mats); free(lights); return throw_brt(env, ctx, BRT_E_NOMEM); }
+    for (size_t i = 0; i < nx; i++) {
+        const double* r = x + 8 * i; texs[i].kind = (int32_t)r[0]; memcpy(texs[i].odd, r + 1, 24); memcpy(texs[i].even, r + 4, 24); texs[i].scale = r[7];
+        for (int k = 0; k < 256; k++) texs[i].perm[k] = xp ? xp[256 * i + k] : (uint8_t)k;
+    }
     for (size_t i = 0; i < nl; i++) { const double* r = l + 8 * i; lights[i].type = (int32_t)r[0]; memcpy(lights[i].v, r + 1, 24); memcpy(lights[i].color, r + 4, 24); lights[i].intensity = r[7]; }
     brt_scene_desc d; memset(&d, 0, sizeof(d));
     d.objects = objs; d.n_objects = (int32_t)no; d.materials = mats; d.n_materials = (int32_t)nm;
     d.mesh_triangles = t; d.n_mesh_triangles = (int64_t)nt; d.lights = lights; d.n_lights = (int32_t)nl;
+    d.textures = texs; d.n_textures = (int32_t)nx;
     int rc = brt_scene_set_flat(ctx, &d);                       /* borrowed, copied before return */
-    free(objs); free(mats); free(lights);
+    free(objs); free(mats); free(lights); free(texs);
     if (rc != BRT_OK) return throw_brt(env, ctx, rc);
     napi_value u; napi_get_undefined(env, &u); return u;
 }

@@ -18,7 +18,8 @@ const require = createRequire(import.meta.url);
 const addon = require('./brt_addon.node');
 
 const OBJ = { Sphere: 0, Plane: 1, Box: 2, Triangle: 3, TriangleMesh: 4 };
-const MAT = { Lambertian: 0, Metal: 1, Dielectric: 2, Emissive: 3 };
+const MAT = { Lambertian: 0, Metal: 1, Dielectric: 2, Emissive: 3, TexturedLambertian: 0, TexturedMetal: 1 };
+const TEX = { SolidColor: 0, CheckerTexture: 1, NoiseTexture: 2, MarbleTexture: 3, WoodTexture: 4 };
 const AA = { none: 0, supersampling: 1, stochastic: 2 };            // any other string: pixel-centre samples (3)
 const TONEMAP = { reinhard: 0, aces: 1, linear: 2 };
 const CAM = { perspective: 0, orthographic: 1 };                     // any other string: 2 (camera.js:25 vs :39)
@@ -27,16 +28,25 @@ const v3 = (v) => [v.x, v.y, v.z];
 
 // world.objects / world.lights -> rows (one per object, IN ORDER: the row index is the object ID, world.js:24-30)
 export function flattenWorld(world) {
-  const objects = [], materials = [], tris = [], lights = [];
+  const objects = [], materials = [], tris = [], lights = [], textures = [], perms = [];
   let firstTri = 0;
   for (const o of world.objects) {
     const kind = o.constructor.name;
     const m = o.material, mk = m.constructor.name;
-    const color = mk === 'Emissive' ? m.color : (mk === 'Dielectric' ? { x: 1, y: 1, z: 1 } : m.albedo);
-    const param = mk === 'Metal' ? m.roughness : mk === 'Dielectric' ? m.refractionIndex : mk === 'Emissive' ? m.intensity : 0;
-    if (!(mk in MAT)) throw new Error(`unsupported material ${mk} (textured materials are never instantiated by the reference)`);
-    materials.push(MAT[mk], ...v3(color), param);
-    const mat = materials.length / 5 - 1;
+    const one = { x: 1, y: 1, z: 1 };
+    const color = mk === 'Emissive' ? m.color : (m.albedo ?? one);
+    const param = (mk === 'Metal' || mk === 'TexturedMetal') ? m.roughness : mk === 'Dielectric' ? m.refractionIndex : mk === 'Emissive' ? m.intensity : 0;
+    if (!(mk in MAT)) throw new Error(`unsupported material ${mk}`);
+    let tex = 0;
+    if (m.texture) {                                                  // TexturedLambertian / TexturedMetal (materials.js:99-126)
+      const t = m.texture, tk = t.constructor.name;
+      if (!(tk in TEX)) throw new Error(`unsupported texture ${tk}`);
+      textures.push(TEX[tk], ...v3(t.odd ?? t.color ?? one), ...v3(t.even ?? one), t.scale ?? 1);
+      perms.push(...(t.noise ? t.noise.p.slice(0, 256) : Array.from({ length: 256 }, (_, i) => i)));
+      tex = textures.length / 8;                                     // 1-based
+    }
+    materials.push(MAT[mk], ...v3(color), param, tex);
+    const mat = materials.length / 6 - 1;
     const z = [0, 0, 0];
     if (kind === 'Sphere') objects.push(OBJ.Sphere, mat, ...v3(o.center), o.radius, 0, 0, ...z, 0, 0);
     else if (kind === 'Plane') objects.push(OBJ.Plane, mat, ...v3(o.point), ...v3(o.normal), ...z, 0, 0);
@@ -53,7 +63,8 @@ export function flattenWorld(world) {
     const point = l.constructor.name === 'PointLight';
     lights.push(point ? 0 : 1, ...v3(point ? l.position : l.direction), ...v3(l.color), l.intensity);
   }
-  return { objects: new Float64Array(objects), materials: new Float64Array(materials), tris: new Float64Array(tris), lights: new Float64Array(lights) };
+  return { objects: new Float64Array(objects), materials: new Float64Array(materials), tris: new Float64Array(tris), lights: new Float64Array(lights),
+    textures: new Float64Array(textures), perms: Uint8Array.from(perms) };
 }
 
 // the Camera object's own derived members (camera.js:14-35): no libm call is repeated on the native side
@@ -97,7 +108,7 @@ export function installGpuRender(RayTracer, { device = 0, seed = 1 } = {}) {
     this._brt ??= addon.create(device);
     const ctx = this._brt;
     const flat = flattenWorld(this.world);
-    addon.setSceneFlat(ctx, flat.objects, flat.materials, flat.tris, flat.lights);
+    addon.setSceneFlat(ctx, flat.objects, flat.materials, flat.tris, flat.lights, flat.textures, flat.perms);
     addon.setCameraDerived(ctx, flattenCamera(this.camera));
     const bg = backgroundOf(this);
     const perm = this.world.cloudNoise ? Uint8Array.from(this.world.cloudNoise.p.slice(0, 256)) : undefined;

@@ -140,10 +140,14 @@ struct HitRecord {                                                              
 struct Scatter { Ray scattered; Vec3 attenuation; };
 enum MatType { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_EMISSIVE = 3 };
 
+struct Texture;                                                                        // js/textures.js (defined after PerlinNoise)
+Vec3 texture_value(const Texture* t, const Vec3& p);
+
 struct Material {
     int type;
     Vec3 color;        // albedo / emissive colour
     double p;          // roughness | refractionIndex | intensity
+    const Texture* tex = nullptr;   // TexturedLambertian / TexturedMetal (materials.js:99-126): attenuation = texture.value(u, v, point)
     Material(int t, const Vec3& c, double p_) : type(t), color(c), p(p_) {
         if (type == MAT_METAL) p = js_min(p_, 1);                                      // materials.js:33
     }
@@ -153,13 +157,13 @@ struct Material {
         case MAT_LAMBERTIAN: {                                                         // materials.js:20-25
             Vec3 scatterDirection = rec.normal.add(Vec3::randomInUnitSphere(g).normalize());
             out.scattered = Ray(rec.point, scatterDirection);
-            out.attenuation = color;
+            out.attenuation = tex ? texture_value(tex, rec.point) : color;                 // materials.js:109
             return true;
         }
         case MAT_METAL: {                                                              // materials.js:36-41
             Vec3 reflected = ray.direction.normalize().reflect(rec.normal);
             out.scattered = Ray(rec.point, reflected.add(Vec3::randomInUnitSphere(g).mul(p)));
-            out.attenuation = color;
+            out.attenuation = tex ? texture_value(tex, rec.point) : color;                 // materials.js:124
             return out.scattered.direction.dot(rec.normal) > 0;
         }
         case MAT_DIELECTRIC: {                                                         // materials.js:51-70
@@ -434,6 +438,40 @@ struct PerlinNoise {
     }
 };
 
+// ---------------------------------------------------------------- js/textures.js
+// Every texture's value(u, v, p) ignores u and v and uses only the hit point p (textures.js:21,33-36,47-50,61-65,77-82).
+enum TexKind { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_MARBLE = 3, TEX_WOOD = 4 };
+struct Texture {
+    int kind = TEX_SOLID;
+    Vec3 odd, even;      // SolidColor.color lives in `odd`
+    double scale = 1;
+    PerlinNoise noise;   // each noise-based texture owns a PerlinNoise (random permutation in the reference: an input here)
+};
+Vec3 texture_value(const Texture* t, const Vec3& p) {
+    switch (t->kind) {
+    case TEX_CHECKER: {                                                                // textures.js:33-36
+        double sines = std::sin(t->scale * p.x) * std::sin(t->scale * p.y) * std::sin(t->scale * p.z);
+        return sines < 0 ? t->odd : t->even;
+    }
+    case TEX_NOISE: {                                                                  // textures.js:47-50
+        double n = t->noise.noise(p.mul(t->scale));
+        return Vec3(1, 1, 1).mul(0.5 * (1 + n));
+    }
+    case TEX_MARBLE: {                                                                 // textures.js:61-65
+        double n = t->noise.turbulence(p.mul(t->scale), 7);
+        double marble = 0.5 * (1 + std::sin(t->scale * p.z + 10 * n));
+        return Vec3(0.9, 0.8, 0.7).mul(marble).add(Vec3(0.6, 0.4, 0.3).mul(1 - marble));
+    }
+    case TEX_WOOD: {                                                                   // textures.js:77-82
+        double grain = t->noise.noise(p.mul(t->scale * 20));
+        double rings = std::sin(t->scale * std::sqrt(p.x * p.x + p.z * p.z) + grain * 10);
+        double wood = 0.5 * (1 + rings);
+        return Vec3(0.8, 0.5, 0.2).mul(wood).add(Vec3(0.4, 0.2, 0.1).mul(1 - wood));
+    }
+    default: return t->odd;                                                            // textures.js:21
+    }
+}
+
 // ---------------------------------------------------------------- js/camera.js
 enum CamType { CAM_PERSPECTIVE = 0, CAM_ORTHOGRAPHIC = 1, CAM_OTHER = 2 };
 struct Camera {
@@ -495,6 +533,7 @@ enum BgKind { BG_GRADIENT = 0, BG_SOLID = 1, BG_HDRI = 2, BG_PROCEDURAL_SKY = 3 
 struct World {
     std::vector<std::unique_ptr<Hittable>> objects;
     std::vector<std::unique_ptr<Material>> materials;
+    std::vector<std::unique_ptr<Texture>> textures;
     std::vector<Light> lights;
     int background = BG_GRADIENT;                                                      // world.js:12
     Vec3 solidColor = Vec3(0.1, 0.1, 0.1);
@@ -810,6 +849,22 @@ void orc_set_background(void* s_, int kind, const double* color, double intensit
     s->world.background = kind;
     if (color) s->world.solidColor = Vec3(color[0], color[1], color[2]);
     s->world.skyIntensity = intensity;
+}
+// new TexturedLambertian(texture) / new TexturedMetal(texture, roughness) on object `obj` (materials.js:99-126)
+int orc_set_object_texture(void* s_, int obj, int kind, const double* odd, const double* even, double scale, const int* perm256) {
+    Scene* s = (Scene*)s_;
+    if (obj < 0 || obj >= (int)s->world.objects.size() || kind < 0 || kind > 4) return -1;
+    s->world.textures.emplace_back(new Texture());
+    Texture* t = s->world.textures.back().get();
+    t->kind = kind; t->odd = Vec3(odd[0], odd[1], odd[2]); t->even = Vec3(even[0], even[1], even[2]); t->scale = scale;
+    if (perm256) for (int i = 0; i < 256; i++) { t->noise.p[i] = perm256[i] & 255; t->noise.p[256 + i] = perm256[i] & 255; }
+    const_cast<Material*>(s->world.objects[obj]->material)->tex = t;
+    return 0;
+}
+void orc_texture_value(void* s_, int obj, const double* p, double* out3) {
+    Scene* s = (Scene*)s_;
+    Vec3 c = texture_value(s->world.objects[obj]->material->tex, Vec3(p[0], p[1], p[2]));
+    out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
 }
 void orc_set_perm(void* s_, const int* perm256) {                                      // noise.js:6-18 (shuffle result supplied)
     Scene* s = (Scene*)s_;

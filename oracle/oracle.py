@@ -94,6 +94,8 @@ def lib():
     L.orc_refract.argtypes = [dp, dp, C.c_double, dp]
     L.orc_denoise.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_float)]
     L.orc_quantize_image.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    L.orc_set_object_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp, C.c_double, C.POINTER(C.c_int)]
+    L.orc_texture_value.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.orc_philox_raw.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_rng_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, dp]
     L.orc_render_rect.argtypes = [C.c_void_p, C.POINTER(_RenderParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -234,6 +236,22 @@ class OracleScene:
         self.sky_intensity = float(intensity)
         self.solid_color = tuple(float(c) for c in color)
         self.L.orc_set_background(self.h, BG[self.bg_kind], _d3(color), float(intensity))
+
+    TEX = {"solid": 0, "checker": 1, "noise": 2, "marble": 3, "wood": 4}
+
+    def set_object_texture(self, obj, kind, odd=(1, 1, 1), even=(1, 1, 1), scale=1.0, perm256=None):
+        """Replace object `obj`'s Lambertian / Metal by its Textured* variant (materials.js:99-126) with this texture."""
+        perm = None
+        if perm256 is not None:
+            perm = (C.c_int * 256)(*[int(x) for x in perm256])
+        rc = self.L.orc_set_object_texture(self.h, int(obj), self.TEX[kind], _d3(odd), _d3(even), float(scale), perm)
+        assert rc == 0
+        return rc
+
+    def texture_value(self, obj, p):
+        out = (C.c_double * 3)()
+        self.L.orc_texture_value(self.h, int(obj), _d3(p), out)
+        return np.array(out[:])
 
     def set_perm(self, perm256):
         p = np.ascontiguousarray(np.asarray(perm256, dtype=np.int32))
