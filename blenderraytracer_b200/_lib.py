@@ -93,6 +93,7 @@ SIGNATURES = {
     "brt_last_error": (C.c_char_p, [C.c_void_p]),
     "brt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "brt_scene_load_json": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "brt_scene_load_binary": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "brt_scene_set_flat": (C.c_int, [C.c_void_p, C.POINTER(brt_scene_desc)]),
     "brt_scene_get_flat": (C.c_int, [C.c_void_p, C.POINTER(brt_scene_desc)]),
     "brt_scene_info_get": (C.c_int, [C.c_void_p, C.POINTER(brt_scene_info)]),

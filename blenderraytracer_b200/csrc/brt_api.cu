@@ -153,12 +153,13 @@ static int validate_scene(brt_ctx* ctx, const HostScene& s) {
     return BRT_OK;
 }
 
-int brt_scene_load_json(brt_ctx* ctx, const char* utf8, size_t len, int fw, int fh, int* out_has_camera, int* out_w, int* out_h) {
-    if (!ctx || !utf8) return BRT_E_INVALID;
+static int scene_load_common(brt_ctx* ctx, const void* data, size_t len, bool binary, int fw, int fh, int* out_has_camera, int* out_w, int* out_h) {
+    if (!ctx || !data) return BRT_E_INVALID;
     if (fw <= 0 || fh <= 0) return fail(ctx, BRT_E_INVALID, "fallback width/height must be positive");
     HostScene sc; bool hasCam = false; int w = 0, h = 0; std::string err;
     brt_camera cam = ctx->cam; HostBackground bg = ctx->bg;
-    int rc = load_scene_json(utf8, len, fw, fh, sc, bg, cam, hasCam, w, h, err);
+    int rc = binary ? load_scene_binary((const unsigned char*)data, len, fw, fh, sc, bg, cam, hasCam, w, h, err)
+                    : load_scene_json((const char*)data, len, fw, fh, sc, bg, cam, hasCam, w, h, err);
     if (rc != BRT_OK) return fail(ctx, rc, err);
     if ((rc = validate_scene(ctx, sc)) != BRT_OK) return rc;
     ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true;
@@ -168,6 +169,12 @@ int brt_scene_load_json(brt_ctx* ctx, const char* utf8, size_t len, int fw, int 
     if (out_w) *out_w = w;
     if (out_h) *out_h = h;
     return BRT_OK;
+}
+int brt_scene_load_json(brt_ctx* ctx, const char* utf8, size_t len, int fw, int fh, int* out_has_camera, int* out_w, int* out_h) {
+    return scene_load_common(ctx, utf8, len, false, fw, fh, out_has_camera, out_w, out_h);
+}
+int brt_scene_load_binary(brt_ctx* ctx, const void* bytes, size_t len, int fw, int fh, int* out_has_camera, int* out_w, int* out_h) {
+    return scene_load_common(ctx, bytes, len, true, fw, fh, out_has_camera, out_w, out_h);
 }
 
 int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {

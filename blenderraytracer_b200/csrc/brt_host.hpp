@@ -29,4 +29,8 @@ void derive_camera(brt_camera& c);
 int load_scene_json(const char* utf8, size_t len, int fallbackW, int fallbackH, HostScene& scene, HostBackground& bg,
                     brt_camera& cam, bool& hasCamera, int& outW, int& outH, std::string& err);
 
+// Binary container "BRTSCN01": the same scene JSON with mesh arrays moved into a blob (see scene_loader.cpp).
+int load_scene_binary(const unsigned char* bytes, size_t len, int fallbackW, int fallbackH, HostScene& scene, HostBackground& bg,
+                      brt_camera& cam, bool& hasCamera, int& outW, int& outH, std::string& err);
+
 }  // namespace brt

@@ -6,6 +6,7 @@
 // Array.isArray, and arithmetic coercion of null/booleans.  Values outside docs/scene_format.md (strings where
 // numbers belong) become NaN.
 #include <cmath>
+#include <cstring>
 #include <limits>
 #include "brt_host.hpp"
 #include "json.hpp"
@@ -83,6 +84,20 @@ static void fetch_vertex(const std::vector<double>& verts, size_t nverts, double
     set3(out, verts[3 * k], verts[3 * k + 1], verts[3 * k + 2]);
 }
 
+// Binary container (brt_scene_load_binary): mesh arrays may live in a blob after the JSON header instead of as JSON text.
+struct Blob { const unsigned char* p = nullptr; size_t n = 0; };
+static thread_local Blob g_blob;
+
+// {"offset": bytes from blob start, "count": elements} -> pointer, or throws
+static const unsigned char* blob_ref(const Value* ref, size_t elemBytes, size_t& count) {
+    if (!ref || !ref->is_object()) throw LoadError{ "binary mesh reference must be an object {offset, count}" };
+    double off = num(ref->get("offset")), cnt = num(ref->get("count"));
+    if (!(off >= 0) || !(cnt >= 0) || off != std::floor(off) || cnt != std::floor(cnt)) throw LoadError{ "bad binary mesh reference" };
+    if (!g_blob.p || off + cnt * (double)elemBytes > (double)g_blob.n) throw LoadError{ "binary mesh reference outside the blob" };
+    count = (size_t)cnt;
+    return g_blob.p + (size_t)off;
+}
+
 static void create_object(HostScene& sc, const Value& o) {       // scene-loader.js:90-137
     if (!o.is_object()) {
         if (o.kind == brtjson::NUL) throw LoadError{ "cannot read properties of null (reading 'type')" };
@@ -104,6 +119,23 @@ static void create_object(HostScene& sc, const Value& o) {       // scene-loader
         ob.type = BRT_OBJ_BOX; parse_vec3(o.get("min"), ob.a); parse_vec3(o.get("max"), ob.b);
     } else if (t == "triangle") {
         ob.type = BRT_OBJ_TRIANGLE; parse_vec3(o.get("v0"), ob.a); parse_vec3(o.get("v1"), ob.b); parse_vec3(o.get("v2"), ob.c);
+    } else if (t == "mesh" && o.get("vertices_bin")) {
+        // same TriangleMesh rules (geometry.js:206-231) over float64 vertex triples and uint32 indices stored in the blob
+        size_t nvd = 0, ni = 0;
+        const unsigned char* vb = blob_ref(o.get("vertices_bin"), sizeof(double), nvd);
+        const unsigned char* ib = blob_ref(o.get("indices_bin"), sizeof(uint32_t), ni);
+        const size_t nv = nvd / 3;
+        ob.type = BRT_OBJ_MESH; ob.first_tri = (int64_t)(sc.meshTris.size() / 9); ob.tri_count = 0;
+        sc.meshTris.reserve(sc.meshTris.size() + 3 * ni);
+        for (size_t i = 0; i + 2 < ni; i += 3) {
+            uint32_t ix[3];
+            memcpy(ix, ib + 4 * i, 12);
+            if (ix[0] >= nv || ix[1] >= nv || ix[2] >= nv) continue;             // geometry.js:216-219
+            double tri[9];
+            for (int k = 0; k < 3; k++) memcpy(tri + 3 * k, vb + 24 * (size_t)ix[k], 24);
+            sc.meshTris.insert(sc.meshTris.end(), tri, tri + 9);
+            ob.tri_count++;
+        }
     } else if (t == "mesh") {
         const Value* vs = o.get("vertices"); const Value* is = o.get("indices");
         if (!truthy(vs) || !truthy(is)) { sc.materials.pop_back(); return; }  // :120-123
@@ -246,6 +278,23 @@ int load_scene_json(const char* utf8, size_t len, int fallbackW, int fallbackH, 
         err = e.msg;
         return BRT_E_PARSE;
     }
+}
+
+// Container: "BRTSCN01" | u64 json_len (LE) | json (docs/scene_format.md, meshes may carry vertices_bin / indices_bin
+// = {offset, count} instead of vertices / indices) | zero padding to 8 bytes | blob (float64 vertex triples, uint32 indices).
+int load_scene_binary(const unsigned char* bytes, size_t len, int fallbackW, int fallbackH, HostScene& scene, HostBackground& bg,
+                      brt_camera& cam, bool& hasCamera, int& outW, int& outH, std::string& err) {
+    if (len < 16 || memcmp(bytes, "BRTSCN01", 8) != 0) { err = "not a BRTSCN01 container"; return BRT_E_PARSE; }
+    uint64_t jl = 0;
+    memcpy(&jl, bytes + 8, 8);
+    if (jl > len - 16) { err = "truncated BRTSCN01 container"; return BRT_E_PARSE; }
+    size_t blobAt = 16 + (size_t)jl;
+    blobAt = (blobAt + 7) & ~(size_t)7;
+    g_blob.p = blobAt <= len ? bytes + blobAt : nullptr;
+    g_blob.n = blobAt <= len ? len - blobAt : 0;
+    int rc = load_scene_json((const char*)bytes + 16, (size_t)jl, fallbackW, fallbackH, scene, bg, cam, hasCamera, outW, outH, err);
+    g_blob = Blob{};
+    return rc;
 }
 
 }  // namespace brt

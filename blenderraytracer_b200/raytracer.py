@@ -201,9 +201,13 @@ class RayTracer:
         self.setupDefaultScene()
 
     def loadFromJSON(self, jsonData) -> bool:                          # ray-tracer.js:305-334
-        """`jsonData`: the parsed scene (dict) as the reference receives it, or the JSON text itself (str / bytes)."""
+        """`jsonData`: the parsed scene (dict) as the reference receives it, the JSON text itself (str / bytes), or a
+        BRTSCN01 binary container (bytes)."""
+        binary = False
         if isinstance(jsonData, (bytes, bytearray)):
             text = bytes(jsonData)
+            if text[:8] == b"BRTSCN01":                                # binary container (tools/scene_binary.py)
+                binary = True
         elif isinstance(jsonData, str):
             text = jsonData.encode("utf-8")
         else:
@@ -212,7 +216,8 @@ class RayTracer:
             except (TypeError, ValueError):
                 return False
         has_cam, w, h = C.c_int(0), C.c_int(0), C.c_int(0)
-        rc = self._L.brt_scene_load_json(self._ctx, text, len(text), self.width, self.height, C.byref(has_cam), C.byref(w), C.byref(h))
+        load = self._L.brt_scene_load_binary if binary else self._L.brt_scene_load_json
+        rc = load(self._ctx, text, len(text), self.width, self.height, C.byref(has_cam), C.byref(w), C.byref(h))
         if rc != L.BRT_OK:                                             # the reference logs and returns false (:330-333)
             self.lastError = self._L.brt_last_error(self._ctx).decode("utf-8", "replace")
             return False

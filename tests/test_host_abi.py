@@ -348,3 +348,34 @@ def test_scene_generators_are_deterministic():
     # triangles of the C5 grid are large enough that the reference's absolute |a| < 1e-4 cull (geometry.js:157) stays negligible
     e = np.linalg.norm(V5[I5[1]] - V5[I5[0]])
     assert e > 0.25
+
+
+def test_binary_container_ingest_equals_json(host, sample_mesh):
+    """the BRTSCN01 container (tools/scene_binary.py) ingests to exactly the scene the JSON gives,
+    including TriangleMesh's index filtering; malformed containers are rejected like malformed JSON."""
+    from tools import gen_scenes, scene_binary
+    lib, h = host
+    ragged = json.loads(json.dumps(sample_mesh))
+    ragged["objects"][0]["indices"] = ragged["objects"][0]["indices"][:-3] + [0, 1, 99, 2, 3]     # out-of-range triple + incomplete tail
+    for scene in (sample_mesh, ragged, gen_scenes.cornell(), gen_scenes.terrain(quads=20)):
+        snap = lambda objs: [(a.type, a.material, a.first_tri, a.tri_count, list(a.a), list(a.b), list(a.c)) for a in objs]
+        assert _load(lib, h, scene)[0] == L.BRT_OK
+        o1, m1, l1, t1 = _flat(lib, h)
+        o1, m1, l1 = snap(o1), len(m1), len(l1)          # the pointers are borrowed from the ctx: copy before the next load
+        data = scene_binary.pack(scene)
+        hc, w, hh = C.c_int(), C.c_int(), C.c_int()
+        assert lib.brt_scene_load_binary(h, data, len(data), 600, 400, C.byref(hc), C.byref(w), C.byref(hh)) == L.BRT_OK, lib.brt_last_error(h)
+        o2, m2, l2, t2 = _flat(lib, h)
+        assert np.array_equal(t1, t2) and o1 == snap(o2) and m1 == len(m2) and l1 == len(l2)
+        assert hc.value == 1
+    big = gen_scenes.terrain(quads=64)
+    assert len(scene_binary.pack(big)) < 0.85 * len(json.dumps(big))                    # smaller, and no text parse
+    data = scene_binary.pack(sample_mesh)
+    for bad in (data[:12], b"BRTSCN02" + data[8:], data[:-40], b"BRTSCN01" + (2 ** 40).to_bytes(8, "little") + data[16:]):
+        assert lib.brt_scene_load_binary(h, bad, len(bad), 600, 400, None, None, None) == L.BRT_E_PARSE
+        assert lib.brt_last_error(h)
+    # the Python mirror picks the loader from the magic
+    import torch
+    if torch.cuda.is_available():
+        rt = brt.RayTracer(64, 48)
+        assert rt.loadFromJSON(data) and rt.sceneInfo()["n_triangles"] == 12
