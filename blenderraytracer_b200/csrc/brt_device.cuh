@@ -86,9 +86,10 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm
 
 // ------------------------------------------------------------------------------------------- Philox4x32-10
 // Stands in for Math.random (math.js:21-31).  counter = (pixel, sample, block, tag), key = seed.
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < ROUNDS; r++) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -97,6 +98,25 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     }
     return make_uint4(c0, c1, c2, c3);
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32<10>(c0, c1, c2, c3, k0, k1);
+}
+// The fast sampler's generator.  Philox4x32-7 is the fewest rounds that pass BigCrush (Salmon et al., SC'11, table 2);
+// -10 is Random123's safety-margin default and what the sequential (reference) sampler and the oracle use.
+#ifndef BRT_PHILOX_FAST_ROUNDS
+#define BRT_PHILOX_FAST_ROUNDS 10
+#endif
+__device__ __forceinline__ uint4 philox_fast(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32<BRT_PHILOX_FAST_ROUNDS>(c0, c1, c2, c3, k0, k1);
+}
+// Reciprocal used by the fp32 intersection code: the 1-ulp MUFU approximation (one instruction instead of the ~8 of the
+// IEEE sequence; +6 % on C3).  Deterministic, so brute force and BVH still agree bit for bit; primary-hit t / normals that
+// are compared with the float64 reference come from refine_primary, not from here.  -DBRT_IEEE_RCP restores __frcp_rn.
+#ifdef BRT_IEEE_RCP
+__device__ __forceinline__ float rcpf(float x) { return __frcp_rn(x); }
+#else
+__device__ __forceinline__ float rcpf(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 constexpr uint32_t PHILOX_TAG = 0x42525431u;   // "BRT1"
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
@@ -127,7 +147,7 @@ struct RngSeq {
 
 // geometry.js:15-29.  Discriminant evaluated as a*(r^2 - |oc - (hb/a) D|^2) (cancellation-robust form of hb^2 - a c).
 __device__ __forceinline__ bool hit_sphere(float4 s, float3 O, float3 D, float tMin, bool self, float& t) {
-    float a = dot(D, D), inva = __frcp_rn(a);
+    float a = dot(D, D), inva = rcpf(a);
     float3 oc = O - f3(s.x, s.y, s.z);
     float hb = dot(oc, D);
     if (self) { t = __fmul_rn(__fmul_rn(-2.f, hb), inva); return t >= tMin; }
@@ -157,7 +177,7 @@ __device__ __forceinline__ bool hit_plane(float4 n, float4 p, float3 O, float3 D
 // geometry.js:85-112.  `face` returns 0..5 = x-,x+,y-,y+,z-,z+ : the slab plane that produced t (the reference picks
 // the face by |p - face| < 1e-6, :119-126, which is the same face away from edges; ties resolve x, y, z as there).
 __device__ __forceinline__ bool hit_box(float4 mn, float4 mx, float3 O, float3 D, float tMin, bool self, float& t, int& face) {
-    float3 inv = f3(__frcp_rn(D.x), __frcp_rn(D.y), __frcp_rn(D.z));
+    float3 inv = f3(rcpf(D.x), rcpf(D.y), rcpf(D.z));
     float t0 = __fmul_rn(mn.x - O.x, inv.x), t1 = __fmul_rn(mx.x - O.x, inv.x);
     int fe = 0, fx = 1;                         // entering / exiting face ids
     if (t0 > t1) { float tmp = t0; t0 = t1; t1 = tmp; fe = 1; fx = 0; }
@@ -192,7 +212,7 @@ __device__ __forceinline__ bool hit_tri(float4 v0, float4 e1, float4 e2, float3 
     float3 h = cross(D, E2);
     float a = dot(E1, h);
     if (fabsf(a) < 0.0001f) return false;
-    float f = __frcp_rn(a);
+    float f = rcpf(a);
     float3 s = O - xyz(v0);
     float u = __fmul_rn(f, dot(s, h));
     if (u < 0.f || u > 1.f) return false;
@@ -296,7 +316,7 @@ constexpr uint32_t TRAV_DONE = 0xFFFFFFFFu;
 struct RayInv { float3 inv, ood; };
 __device__ __forceinline__ RayInv ray_inv(float3 O, float3 D) {
     RayInv r;
-    r.inv = f3(__frcp_rn(D.x), __frcp_rn(D.y), __frcp_rn(D.z));
+    r.inv = f3(rcpf(D.x), rcpf(D.y), rcpf(D.z));
     r.ood = O * r.inv;
     return r;
 }
@@ -467,7 +487,7 @@ __device__ __forceinline__ Surface make_surface(const DevScene& sc, const Hit& h
     float3 n;
     if (ty == PT_SPHERE) {
         float4 sp = ldg4(sc.sph + ix);
-        n = (s.P - f3(sp.x, sp.y, sp.z)) * __frcp_rn(sp.w);                    // geometry.js:34 (negative radius flips)
+        n = (s.P - f3(sp.x, sp.y, sp.z)) * rcpf(sp.w);                    // geometry.js:34 (negative radius flips)
     } else if (ty == PT_PLANE) {
         n = xyz(ldg4(sc.pln + 2 * ix));
     } else if (ty == PT_BOX) {

@@ -55,7 +55,7 @@ __device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t p
     CamSample cs; cs.s = 0.f; cs.t = 0.f;
     float a0 = 0.f, a1 = 0.f;
     if (SAMPLER == 0) {
-        uint4 r = philox4x32_10(pix, s, 0u, PHILOX_TAG, p.seedLo, p.seedHi);
+        uint4 r = philox_fast(pix, s, 0u, PHILOX_TAG, p.seedLo, p.seedHi);
         a0 = u01(r.x); a1 = u01(r.y);
         float rr = sqrtf(u01(r.z)), sn, cs_;                   // unit disk by inversion (math.js:27-31 distribution)
         sincospif(__fmul_rn(2.f, u01(r.w)), &sn, &cs_);
@@ -82,7 +82,7 @@ __device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m
     const int matType = matWord & 255, tex = matWord >> 8;           // 1-based texture index above the type (materials.js:99-126)
     float u0 = 0.f, u1 = 0.f, u2 = 0.f;
     if (SAMPLER == 0) {
-        uint4 r = philox4x32_10(pix, s, (uint32_t)(bounce + 1), PHILOX_TAG, p.seedLo, p.seedHi);
+        uint4 r = philox_fast(pix, s, (uint32_t)(bounce + 1), PHILOX_TAG, p.seedLo, p.seedHi);
         u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z);
     }
     if (matType == 0) {                                                       // Lambertian (materials.js:20-25)
