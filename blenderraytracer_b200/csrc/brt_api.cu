@@ -36,7 +36,7 @@ struct brt_ctx {
     brt_render_params rp{};
     // device scene
     DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm, dPrim64, dTex, dTexPerm;
-    float4* dNodes = nullptr;
+    BvhWorkspace bvhWs;
     DevScene dev{};
     bool sceneDirty = true, permDirty = true;
     int nBounded = 0;
@@ -109,7 +109,7 @@ void brt_destroy(brt_ctx* ctx) {
                        &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch, &ctx->dPlanes,
                        &ctx->dObj64, &ctx->dTris64 };
     for (DevBuf* b : bufs) b->release();
-    if (ctx->dNodes) cudaFree(ctx->dNodes);
+    free_bvh_workspace(&ctx->bvhWs);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -220,14 +220,19 @@ static int upload_scene(brt_ctx* ctx) {
     size_t nTriTotal = 0;
     for (const brt_object& o : s.objects) nTriTotal += o.type == BRT_OBJ_TRIANGLE ? 1 : o.type == BRT_OBJ_MESH ? (size_t)o.tri_count : 0;
     if (nTriTotal >= (1u << 28) || s.objects.size() >= (1u << 28)) return fail(ctx, BRT_E_INVALID, "too many primitives (limit 2^28 per type)");
-    tri.reserve(3 * nTriTotal); mTri.reserve(nTriTotal);
+    // triangles dominate large scenes: sized once, filled by index (no per-triangle push_back / insert)
+    tri.resize(3 * nTriTotal); mTri.resize(nTriTotal); qTri.resize(9 * nTriTotal);
+    size_t triAt = 0;
     auto push_tri = [&](const double* v0, const double* v1, const double* v2, int obj, int m, int triId) {
-        tri.push_back(f4(v0[0], v0[1], v0[2], 0));
+        float4* t = &tri[3 * triAt];
+        t[0] = f4(v0[0], v0[1], v0[2], 0);
         // edges are formed in float64 and rounded once (geometry.js:150-151 recomputes them per hit in float64)
-        tri.push_back(f4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], 0));
-        tri.push_back(f4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0));
-        mTri.push_back(make_int4(obj, m, triId, 0));
-        qTri.insert(qTri.end(), v0, v0 + 3); qTri.insert(qTri.end(), v1, v1 + 3); qTri.insert(qTri.end(), v2, v2 + 3);
+        t[1] = f4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], 0);
+        t[2] = f4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0);
+        mTri[triAt] = make_int4(obj, m, triId, 0);
+        double* q = &qTri[9 * triAt];
+        memcpy(q, v0, 24); memcpy(q + 3, v1, 24); memcpy(q + 6, v2, 24);
+        triAt++;
     };
     auto push9 = [](std::vector<double>& q, const double* a, const double* b, const double* c) {
         static const double z[3] = { 0, 0, 0 };
@@ -296,16 +301,14 @@ static int upload_scene(brt_ctx* ctx) {
     d.tex = (const float4*)ctx->dTex.p; d.texPerm = (const unsigned char*)ctx->dTexPerm.p; d.nTex = (int)s.textures.size();
     auto t1 = std::chrono::steady_clock::now();
     // LBVH over the bounded primitives
-    if (ctx->dNodes) { cudaFree(ctx->dNodes); ctx->dNodes = nullptr; }
     d.nodes = nullptr; d.nNodes = 0;
     ctx->nBounded = d.nSph + d.nBox + d.nTri;
     BvhBuildResult br{};
-    CK(build_lbvh(d, &br, ctx->stream));
+    CK(build_lbvh(d, &ctx->bvhWs, &br, ctx->stream));
     if (br.depth > SMEM_STACK + LOCAL_STACK) {
-        if (br.nodes) cudaFree(br.nodes);
         return fail(ctx, BRT_E_STATE, "LBVH deeper than the traversal stack (" + std::to_string(br.depth) + ")");
     }
-    ctx->dNodes = br.nodes; d.nodes = br.nodes; d.nNodes = (int)br.nNodes; d.bvhStackDepth = br.depth;
+    d.nodes = br.nodes; d.nNodes = (int)br.nNodes; d.bvhStackDepth = br.depth;
     brt_scene_info& inf = ctx->info;
     inf.n_objects = (int)s.objects.size(); inf.n_materials = (int)s.materials.size(); inf.n_lights = (int)s.lights.size();
     inf.n_spheres = d.nSph; inf.n_planes = d.nPln; inf.n_boxes = d.nBox; inf.n_triangles = d.nTri;

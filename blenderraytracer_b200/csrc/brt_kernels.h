@@ -69,13 +69,18 @@ cudaError_t launch_primary_aov64(const Obj64* objs, int nObjs, const double* mes
                                  int* objId, int* triId, double* t, double* nrm, unsigned char* front, cudaStream_t st);
 
 // bvh.cu — GPU LBVH: Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit
+struct BvhWorkspace {            // grow-only build memory, owned by the ctx (free_bvh_workspace at destroy)
+    void* arena = nullptr; size_t arenaCap = 0;
+    float4* nodes[2] = { nullptr, nullptr }; size_t nodeCap[2] = { 0, 0 };
+};
+void free_bvh_workspace(BvhWorkspace* ws);
 struct BvhBuildResult {
-    float4* nodes;               // device, 4 x float4 per node, root = 0 (cudaMalloc'd; caller frees)
+    float4* nodes;               // device, 4 x float4 per node, root = 0 (points into the workspace: do not free)
     long long nNodes;
     int depth;
     float buildMs;
 };
 // prim AABBs are computed on the device from the SoA arrays; pids = primitive ids of the bounded primitives
-cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st);
+cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out, cudaStream_t st);
 
 }  // namespace brt

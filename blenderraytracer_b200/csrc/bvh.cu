@@ -265,37 +265,58 @@ __global__ void __launch_bounds__(256) k_sah_cost(const Aabb* nodeBox, int nInte
 
 #define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return e_; } } while (0)
 
-cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st) {
+void free_bvh_workspace(BvhWorkspace* ws) {
+    if (!ws) return;
+    cudaFree(ws->arena); cudaFree(ws->nodes[0]); cudaFree(ws->nodes[1]);
+    *ws = BvhWorkspace{};
+}
+
+// All build memory lives in `ws` (grow-only, owned by the ctx): one scratch arena carved into the temporaries plus two
+// node buffers for the two candidate trees, so re-building for a new scene of similar size allocates nothing
+// (cudaMalloc / cudaFree of ~100 MB blocks cost far more than the 1 ms build itself).
+cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out, cudaStream_t st) {
     out->nodes = nullptr; out->nNodes = 0; out->depth = 0; out->buildMs = 0.f;
     const int n = sc.nSph + sc.nBox + sc.nTri;
     if (n < 2) return cudaSuccess;                    // 0 or 1 bounded primitive: traversal falls back to the linear loop
-    Aabb *boxes = nullptr, *nodeBox = nullptr; float *blockBounds = nullptr, *sb = nullptr;
-    uint32_t *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr, *hist = nullptr; unsigned int* flags = nullptr;
-    int2* children = nullptr; int *parent = nullptr, *nodeDepth = nullptr; float4 *nodes = nullptr, *nodesAlt = nullptr; double* blockSums = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    bool ok = false;
     auto cleanup = [&]() {
-        if (!ok) cudaFree(nodes);
-        cudaFree(boxes); cudaFree(nodeBox); cudaFree(blockBounds); cudaFree(sb); cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
-        cudaFree(hist); cudaFree(flags); cudaFree(children); cudaFree(parent); cudaFree(nodeDepth); cudaFree(nodesAlt); cudaFree(blockSums);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
     const int nb = (n + 255) / 256, sortBlocks = (n + SORT_TILE - 1) / SORT_TILE;
-    BVH_CK(cudaMalloc(&boxes, sizeof(Aabb) * n)); BVH_CK(cudaMalloc(&nodeBox, sizeof(Aabb) * (n - 1)));
-    BVH_CK(cudaMalloc(&blockBounds, sizeof(float) * 6 * nb)); BVH_CK(cudaMalloc(&sb, sizeof(float) * 6));
-    BVH_CK(cudaMalloc(&k0, 4 * (size_t)n)); BVH_CK(cudaMalloc(&k1, 4 * (size_t)n)); BVH_CK(cudaMalloc(&v0, 4 * (size_t)n)); BVH_CK(cudaMalloc(&v1, 4 * (size_t)n));
-    BVH_CK(cudaMalloc(&hist, 4 * 256 * (size_t)sortBlocks)); BVH_CK(cudaMalloc(&flags, 4 * (size_t)(n - 1)));
-    BVH_CK(cudaMalloc(&children, sizeof(int2) * (n - 1))); BVH_CK(cudaMalloc(&parent, 4 * (size_t)(2 * n - 1)));
-    BVH_CK(cudaMalloc(&nodeDepth, 4 * (size_t)(n - 1)));
-    BVH_CK(cudaMalloc(&nodes, sizeof(float4) * 4 * (size_t)(n - 1))); BVH_CK(cudaMalloc(&nodesAlt, sizeof(float4) * 4 * (size_t)(n - 1)));
-    BVH_CK(cudaMalloc(&blockSums, sizeof(double) * ((n - 1 + 255) / 256)));
+    const int costBlocks = (n - 1 + 255) / 256;
+    // carve the arena
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+    const size_t oBoxes = take(sizeof(Aabb) * n), oNodeBox = take(sizeof(Aabb) * (n - 1)), oBlockBounds = take(sizeof(float) * 6 * nb),
+                 oSb = take(sizeof(float) * 6), oK0 = take(4 * (size_t)n), oK1 = take(4 * (size_t)n), oV0 = take(4 * (size_t)n), oV1 = take(4 * (size_t)n),
+                 oHist = take(4 * 256 * (size_t)sortBlocks), oFlags = take(4 * (size_t)(n - 1)), oChildren = take(sizeof(int2) * (n - 1)),
+                 oParent = take(4 * (size_t)(2 * n - 1)), oDepth = take(4 * (size_t)(n - 1)), oSums = take(sizeof(double) * costBlocks);
+    if (off > ws->arenaCap) {
+        cudaFree(ws->arena); ws->arena = nullptr; ws->arenaCap = 0;
+        BVH_CK(cudaMalloc(&ws->arena, off));
+        ws->arenaCap = off;
+    }
+    const size_t nodeBytes = sizeof(float4) * 4 * (size_t)(n - 1);
+    for (int k = 0; k < 2; k++) if (nodeBytes > ws->nodeCap[k]) {
+        cudaFree(ws->nodes[k]); ws->nodes[k] = nullptr; ws->nodeCap[k] = 0;
+        BVH_CK(cudaMalloc(&ws->nodes[k], nodeBytes));
+        ws->nodeCap[k] = nodeBytes;
+    }
+    char* A = (char*)ws->arena;
+    Aabb *boxes = (Aabb*)(A + oBoxes), *nodeBox = (Aabb*)(A + oNodeBox);
+    float *blockBounds = (float*)(A + oBlockBounds), *sb = (float*)(A + oSb);
+    uint32_t *k0 = (uint32_t*)(A + oK0), *k1 = (uint32_t*)(A + oK1), *v0 = (uint32_t*)(A + oV0), *v1 = (uint32_t*)(A + oV1), *hist = (uint32_t*)(A + oHist);
+    unsigned int* flags = (unsigned int*)(A + oFlags);
+    int2* children = (int2*)(A + oChildren);
+    int *parent = (int*)(A + oParent), *nodeDepth = (int*)(A + oDepth);
+    double* blockSums = (double*)(A + oSums);
+    float4 *nodes = ws->nodes[0], *nodesAlt = ws->nodes[1];
     BVH_CK(cudaEventCreate(&e0)); BVH_CK(cudaEventCreate(&e1));
     BVH_CK(cudaEventRecord(e0, st));
     k_prim_bounds<<<nb, 256, 0, st>>>(sc, n, boxes, blockBounds);
     k_scene_bounds<<<1, 256, 0, st>>>(blockBounds, nb, sb);
     // two candidate hierarchies (Morton quantisation per axis / uniform); the one with the smaller surface-area cost is kept
-    const int costBlocks = (n - 1 + 255) / 256;
     std::vector<double> hostSums(costBlocks);
     double bestCost = 0.0; int bestMode = -1, bestDepth = 0;
     for (int mode = 0; mode < 2; mode++) {
@@ -323,13 +344,12 @@ cudaError_t build_lbvh(const DevScene& sc, BvhBuildResult* out, cudaStream_t st)
         // (measured: C3 2 % apart, slower tree estimated cheaper), so the uniform-scale tree must win by > 10 % to be taken
         if (bestMode < 0 || cost < 0.9 * bestCost) { bestCost = cost; bestMode = mode; bestDepth = depth; }
     }
-    if (bestMode == 1) { float4* t = nodes; nodes = nodesAlt; nodesAlt = t; }
+    if (bestMode == 1) nodes = nodesAlt;
     BVH_CK(cudaEventRecord(e1, st));
     BVH_CK(cudaGetLastError());
     BVH_CK(cudaEventSynchronize(e1));
     float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
     int depth = bestDepth;
-    ok = true;
     cleanup();
     out->nodes = nodes; out->nNodes = n - 1; out->depth = depth; out->buildMs = ms;
     return cudaSuccess;
