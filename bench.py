@@ -38,6 +38,10 @@ WORKLOADS = {
                desc="sample_scene.json 600x400 16spp depth10"),
     "c2": dict(fixture="sample_mesh.json", W=1280, H=720, spp=64, depth=10,
                desc="sample_mesh.json 1280x720 64spp depth10"),
+    # BASELINE config 2 names "point-light shadow rays": the reference never calls its lights (lights.js has no call site),
+    # so c2 renders as the reference does and c2d adds the direct-lighting EXTENSION (shadow rays to both lights)
+    "c2d": dict(fixture="sample_mesh.json", W=1280, H=720, spp=64, depth=10, direct=True,
+                desc="sample_mesh.json 1280x720 64spp depth10 + direct-lighting extension (point / directional shadow rays)"),
     "c3": dict(gen="c3", W=1920, H=1080, spp=256, depth=10,
                desc="synthetic random-spheres (486 objects, seed 42) 1920x1080 256spp depth10 thin-lens aperture 0.1"),
     "c4": dict(gen="c4", W=1920, H=1080, spp=1024, depth=16,
@@ -121,6 +125,7 @@ def oracle_rate(w, threads: int, budget_s: float, spp: int = 1):
     assert o.loadFromJSON(w["scene"])
     o.resizeCanvas(W, H)
     o.updateRenderSettings(dict(samples=spp, maxBounces=w["depth"]))
+    o.directLighting = bool(w.get("direct"))
     band = max(1, min(H, 4 * max(1, threads)))
     # bands visited in a bit-reversed order so any prefix covers the frame evenly; when the frame is done and budget
     # remains, another pass renders the next sample index of every pixel
@@ -204,6 +209,7 @@ def run_ours(args):
     rt.resizeCanvas(W, H)                                   # aspect = W/H as the UI path does (ray-tracer.js:505)
     rt.updateRenderSettings(dict(samples=spp, maxBounces=depth))
     rt.sampler, rt.accel, rt.integrator = args.sampler, args.accel, args.integrator
+    rt.directLighting = bool(w.get("direct"))
     rt.refillThreshold = args.refill
     rt.pathsInFlight = args.inflight
     info = rt.sceneInfo()

@@ -311,6 +311,7 @@ __device__ __forceinline__ Hit trace_brute(const DevScene& sc, float3 O, float3 
 // free); deeper entries (rare) spill to a per-thread local array.
 constexpr int SMEM_STACK = 12;
 constexpr int LOCAL_STACK = 52;
+constexpr int SMEM_ONLY_MAX_DEPTH = 40;   // trees up to this depth run with the whole stack in shared memory (20 KB / block at 40)
 constexpr uint32_t TRAV_DONE = 0xFFFFFFFFu;
 
 struct RayInv { float3 inv, ood; };
@@ -350,15 +351,17 @@ __device__ __forceinline__ bool node_visit(const float4* __restrict__ nodes, uin
     return h0 | h1;
 }
 
-// Blocking traversal (primary AOVs, shadow rays): runs one ray to completion.
-template <bool COUNT, bool SHADOW>
+// Blocking traversal: runs one ray to completion.  HYBRID = false: the whole stack lives in shared memory (the launcher
+// sized it from the tree depth: depth + 1 entries per thread) and the loop carries no local-memory path at all;
+// HYBRID = true (trees deeper than SMEM_ONLY_MAX_DEPTH): SMEM_STACK entries in shared memory, the rest in a local array.
+template <bool COUNT, bool SHADOW, bool HYBRID = true>
 __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
                                          uint32_t* sstack /* &smem[threadIdx.x] */, int sstride) {
     Hit best; best.t = tMax; best.pid = PID_NONE;
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
     if (sc.nNodes == 0) return best;
     RayInv r = ray_inv(O, D);
-    uint32_t lstack[LOCAL_STACK];
+    uint32_t lstack[HYBRID ? LOCAL_STACK : 1];
     int sp = 0;
     uint32_t cur = 0;
     for (;;) {
@@ -370,7 +373,7 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
             uint32_t nearc, farc; bool both;
             if (node_visit(sc.nodes, cur, r, best.t, nearc, farc, both)) {
                 if (both) {
-                    if (sp < SMEM_STACK) sstack[sp * sstride] = farc; else lstack[sp - SMEM_STACK] = farc;
+                    if (!HYBRID || sp < SMEM_STACK) sstack[sp * sstride] = farc; else lstack[sp - SMEM_STACK] = farc;
                     sp++;
                 }
                 cur = nearc;
@@ -379,7 +382,7 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
         }
         if (sp == 0) break;
         sp--;
-        cur = sp < SMEM_STACK ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
+        cur = (!HYBRID || sp < SMEM_STACK) ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
     }
     return best;
 }

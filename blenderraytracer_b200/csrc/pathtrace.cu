@@ -131,11 +131,11 @@ __device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m
     return false;                                                             // Emissive (materials.js:94)
 }
 
-template <bool USE_BVH, bool COUNT, bool SHADOW>
+template <bool USE_BVH, bool COUNT, bool SHADOW, bool HYBRID = true>
 __device__ __forceinline__ Hit trace(const DevScene& sc, float3 O, float3 D, float tMax, uint32_t self, Counters& cnt,
                                      uint32_t* sstack, int sstride) {
     if (COUNT && !SHADOW) cnt.rays++;
-    if (USE_BVH) return trace_bvh<COUNT, SHADOW>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride);
+    if (USE_BVH) return trace_bvh<COUNT, SHADOW, HYBRID>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride);
     return trace_brute<COUNT, SHADOW>(sc, O, D, 0.001f, tMax, self, cnt);
 }
 
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
 // (profiles/): the wavefront raises SIMD efficiency of the traversal loop (15 -> 22 active lanes per instruction) but pays
 // for it in queue traffic, refill code and L1 capacity lost to shared memory; the megakernel is faster there and is what
 // BRT_INTEGRATOR_AUTO selects.  Both produce the same image up to fp32 summation order.
-template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT>
+template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega(const __grid_constant__ PTParams p) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 } else camera_ray32(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                 beta = f3(1.f, 1.f, 1.f); self = PID_NONE; depth = 0; alive = true;
             }
-            Hit h = trace<USE_BVH, COUNT, false>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK);
+            Hit h = trace<USE_BVH, COUNT, false, HYBRID>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK);
             if (h.pid == PID_NONE) {                                          // ray-tracer.js:122
                 sum = sum + beta * background(sc, D);
                 alive = false;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                     } else { ldir = f3(-l0.x, -l0.y, -l0.z); ldist = CUDART_INF_F; }
                     float cosN = dot(sf.N, ldir);
                     if (!(cosN > 0.f)) continue;
-                    Hit sh = trace<USE_BVH, COUNT, true>(sc, sf.P, ldir, ldist, h.pid, cnt, sstack, PT_BLOCK);
+                    Hit sh = trace<USE_BVH, COUNT, true, HYBRID>(sc, sf.P, ldir, ldist, h.pid, cnt, sstack, PT_BLOCK);
                     if (sh.pid != PID_NONE) continue;
                     sum = sum + beta * (f3(m.x, m.y, m.z) * lcol) * cosN;
                 }
@@ -541,8 +541,11 @@ static cudaError_t launch_pt3(const PTParams& p, dim3 grid, cudaStream_t st) {
         return cudaGetLastError();
     };
     if (!p.wavefront) {
-        size_t smem = USE_BVH ? (size_t)SMEM_STACK * PT_BLOCK * sizeof(uint32_t) : 0;
-        k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT><<<grid, PT_BLOCK, smem, st>>>(p);
+        // the stack: depth + 1 entries per thread, all in shared memory, unless the tree is unusually deep
+        const bool hybrid = USE_BVH && p.sc.bvhStackDepth > SMEM_ONLY_MAX_DEPTH;
+        size_t smem = USE_BVH ? (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 1) * PT_BLOCK * sizeof(uint32_t) : 0;
+        if (hybrid) k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, true><<<grid, PT_BLOCK, smem, st>>>(p);
+        else k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, false><<<grid, PT_BLOCK, smem, st>>>(p);
         return cudaGetLastError();
     }
     switch (p.inflight) {
