@@ -239,7 +239,7 @@ __device__ __forceinline__ int meta_index(const DevScene& sc, uint32_t pid) {
     int base = ty == PT_SPHERE ? sc.baseSph : ty == PT_PLANE ? sc.basePln : ty == PT_BOX ? sc.baseBox : sc.baseTri;
     return base + (int)ix;
 }
-static __device__ __noinline__ bool tie_wins(const DevScene& sc, uint32_t cand, uint32_t cur) {
+static __device__ __forceinline__ bool tie_wins(const DevScene& sc, uint32_t cand, uint32_t cur) {
     int4 mc = __ldg(&sc.meta[meta_index(sc, cand)]);
     int4 mb = __ldg(&sc.meta[meta_index(sc, cur)]);
     if (mc.x != mb.x) return mc.x < mb.x;

@@ -32,6 +32,8 @@ struct PTParams {
 
 // pathtrace.cu
 cudaError_t launch_pathtrace(const PTParams& p, int sampler, bool useBvh, bool count, int zSplit, cudaStream_t st);
+// pathtrace_wave.cu
+cudaError_t launch_pathtrace_wave(const PTParams& p, int sampler, bool useBvh, int zSplit, cudaStream_t st);
 cudaError_t launch_sum_planes(float4* accum, const float4* planes, int nPlanes, size_t px, cudaStream_t st);
 cudaError_t launch_primary_aov(const PTParams& p, bool useBvh, int* objId, int* triId, float* t, float* nrm, unsigned char* front,
                                cudaStream_t st);

@@ -1,0 +1,140 @@
+// Device code shared by the two integrators (pathtrace.cu: megakernel + AOV / utility kernels; pathtrace_wave.cu: the
+// warp-local wavefront): camera sampling (camera.js), materials (materials.js) and the blocking trace wrapper.
+#pragma once
+#include "brt_device.cuh"
+#include "brt_kernels.h"
+
+namespace brt {
+
+
+// ------------------------------------------------------------------------------------------- camera (camera.js:38-51)
+// The lens / pixel sample of one camera ray: s, t (getAntiAliasSample, ray-tracer.js:125-149) and the unit-disk point.
+struct CamSample { float s, t, dx, dy; };
+
+// float64 ray exactly as camera.js:38-51 forms it (operation order kept), from fp32-exact sample values.
+__device__ __forceinline__ void camera_ray64(const DevCamera& c, int W, int H, int aaMode, int col, int jUp, CamSample cs, D3& O, D3& D) {
+    double u, v;
+    if (aaMode == 1) { u = __ddiv_rn(__dadd_rn((double)col, (double)cs.s), (double)W); v = __ddiv_rn(__dadd_rn((double)jUp, (double)cs.t), (double)H); }
+    else if (aaMode == 2) {
+        u = __ddiv_rn(__dadd_rn((double)col + 0.5, __dmul_rn((double)cs.s, 0.5)), (double)W);
+        v = __ddiv_rn(__dadd_rn((double)jUp + 0.5, __dmul_rn((double)cs.t, 0.5)), (double)H);
+    } else { u = __ddiv_rn((double)col + 0.5, (double)W); v = __ddiv_rn((double)jUp + 0.5, (double)H); }
+    double rx = __dmul_rn((double)cs.dx, c.lensRadius), ry = __dmul_rn((double)cs.dy, c.lensRadius);
+    D3 cu = d3(c.cu[0], c.cu[1], c.cu[2]), cv = d3(c.cv[0], c.cv[1], c.cv[2]);
+    D3 ll = d3(c.ll[0], c.ll[1], c.ll[2]), hh = d3(c.h[0], c.h[1], c.h[2]), vv = d3(c.v[0], c.v[1], c.v[2]);
+    if (c.type == 1) {                                          // camera.js:39-43
+        O = d3(c.o[0], c.o[1], c.o[2]) + cu * rx + cv * ry;
+        D = normalize0(ll + hh * u + vv * v - O + d3(c.cw[0], c.cw[1], c.cw[2]) * -1.0);
+    } else {                                                    // camera.js:44-49
+        O = d3(c.o[0], c.o[1], c.o[2]) + (cu * rx + cv * ry);
+        D = ll + hh * u + vv * v - O;
+    }
+}
+
+// fp32 form of the same ray (BRT_SAMPLER_FAST render path: jittered, lens-offset camera samples have no float64 reference
+// to match bit for bit; LLC - origin is formed in float64 on the host side of this call and rounded once).
+__device__ __forceinline__ void camera_ray32(const DevCamera& c, int W, int H, int aaMode, int col, int jUp, CamSample cs, float3& O, float3& D) {
+    float u, v;
+    if (aaMode == 1) { u = __fdiv_rn((float)col + cs.s, (float)W); v = __fdiv_rn((float)jUp + cs.t, (float)H); }
+    else if (aaMode == 2) { u = __fdiv_rn(fmaf(cs.s, 0.5f, (float)col + 0.5f), (float)W); v = __fdiv_rn(fmaf(cs.t, 0.5f, (float)jUp + 0.5f), (float)H); }
+    else { u = __fdiv_rn((float)col + 0.5f, (float)W); v = __fdiv_rn((float)jUp + 0.5f, (float)H); }
+    float rx = __fmul_rn(cs.dx, (float)c.lensRadius), ry = __fmul_rn(cs.dy, (float)c.lensRadius);
+    float3 off = madd(f3((float)c.cv[0], (float)c.cv[1], (float)c.cv[2]), ry, f3((float)c.cu[0], (float)c.cu[1], (float)c.cu[2]) * rx);
+    O = f3((float)c.o[0], (float)c.o[1], (float)c.o[2]) + off;
+    // D = (LLC - origin) + u*H + v*V - off
+    float3 llo = f3((float)(c.ll[0] - c.o[0]), (float)(c.ll[1] - c.o[1]), (float)(c.ll[2] - c.o[2]));
+    D = madd(f3((float)c.v[0], (float)c.v[1], (float)c.v[2]), v, madd(f3((float)c.h[0], (float)c.h[1], (float)c.h[2]), u, llo)) - off;
+    if (c.type == 1) D = normalize0(D - f3((float)c.cw[0], (float)c.cw[1], (float)c.cw[2]));
+}
+
+template <int SAMPLER>
+__device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t pix, uint32_t s, RngSeq& rng) {
+    CamSample cs; cs.s = 0.f; cs.t = 0.f;
+    float a0 = 0.f, a1 = 0.f;
+    if (SAMPLER == 0) {
+        uint4 r = philox_fast(pix, s, 0u, PHILOX_TAG, p.seedLo, p.seedHi);
+        a0 = u01(r.x); a1 = u01(r.y);
+        float rr = sqrtf(u01(r.z)), sn, cs_;                   // unit disk by inversion (math.js:27-31 distribution)
+        sincospif(__fmul_rn(2.f, u01(r.w)), &sn, &cs_);
+        cs.dx = __fmul_rn(rr, cs_); cs.dy = __fmul_rn(rr, sn);
+    } else {
+        rng.init(pix, s, p.seedLo, p.seedHi);
+        if (p.aaMode == 1 || p.aaMode == 2) { a0 = rng.next(); a1 = rng.next(); }
+        do { cs.dx = rng.next() * 2.f - 1.f; cs.dy = rng.next() * 2.f - 1.f; } while (fmaf(cs.dx, cs.dx, __fmul_rn(cs.dy, cs.dy)) >= 1.0f);   // math.js:29
+    }
+    if (p.aaMode == 1) { cs.s = a0; cs.t = a1; }
+    else if (p.aaMode == 2) {                                    // stochastic: disk of radius 0.5 about the pixel centre
+        float sr = sqrtf(a0), sn, c2;
+        sincospif(__fmul_rn(2.f, a1), &sn, &c2);
+        cs.s = __fmul_rn(sr, c2); cs.t = __fmul_rn(sr, sn);
+    }
+    return cs;
+}
+
+// ------------------------------------------------------------------------------------------- materials (materials.js)
+// Returns false when the path ends here (emissive, absorbed metal).  `att` multiplies the throughput.
+template <int SAMPLER>
+__device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m, const Surface& sf, float3 Din, uint32_t pix,
+                                        uint32_t s, int bounce, RngSeq& rng, float3& Dout, float3& att) {
+    const int matType = matWord & 255, tex = matWord >> 8;           // 1-based texture index above the type (materials.js:99-126)
+    float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+    if (SAMPLER == 0) {
+        uint4 r = philox_fast(pix, s, (uint32_t)(bounce + 1), PHILOX_TAG, p.seedLo, p.seedHi);
+        u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z);
+    }
+    if (matType == 0) {                                                       // Lambertian (materials.js:20-25)
+        float3 unit;
+        if (SAMPLER == 0) unit = uniform_sphere(u0, u1);
+        else {
+            float3 q;
+            do { q = f3(rng.next() * 2.f - 1.f, rng.next() * 2.f - 1.f, rng.next() * 2.f - 1.f); } while (dot(q, q) >= 1.0f);
+            unit = normalize0(q);
+        }
+        Dout = sf.N + unit;
+        att = tex ? texture_value(p.sc, tex - 1, sf.P) : f3(m.x, m.y, m.z);
+        return true;
+    }
+    if (matType == 1) {                                                       // Metal (materials.js:36-41)
+        float3 refl = reflect(normalize0(Din), sf.N);
+        float3 ball;
+        if (SAMPLER == 0) ball = uniform_sphere(u0, u1) * cbrtf(u2);
+        else { do { ball = f3(rng.next() * 2.f - 1.f, rng.next() * 2.f - 1.f, rng.next() * 2.f - 1.f); } while (dot(ball, ball) >= 1.0f); }
+        Dout = madd(ball, m.w, refl);
+        att = tex ? texture_value(p.sc, tex - 1, sf.P) : f3(m.x, m.y, m.z);
+        return dot(Dout, sf.N) > 0.f;
+    }
+    if (matType == 2) {                                                       // Dielectric (materials.js:51-83)
+        float ratio = sf.front ? (1.0f / m.w) : m.w;
+        float3 ud = normalize0(Din);
+        float cosT = fminf(-dot(ud, sf.N), 1.0f);
+        float sinT = sqrtf(fmaxf(0.f, fmaf(-cosT, cosT, 1.0f)));
+        bool cannot = __fmul_rn(ratio, sinT) > 1.0f;
+        bool refl = cannot;
+        if (!cannot) {                                                        // the uniform is drawn only here (:62)
+            float r0 = __fdiv_rn(1.f - ratio, 1.f + ratio); r0 = __fmul_rn(r0, r0);
+            float c1 = 1.f - cosT, c2 = __fmul_rn(c1, c1);
+            float R = fmaf(1.f - r0, __fmul_rn(__fmul_rn(c2, c2), c1), r0);
+            float xi = SAMPLER == 0 ? u0 : rng.next();
+            refl = R > xi;
+        }
+        if (refl) Dout = reflect(ud, sf.N);
+        else {
+            float3 perp = madd(sf.N, cosT, ud) * ratio;
+            Dout = madd(sf.N, -sqrtf(fabsf(1.0f - dot(perp, perp))), perp);
+        }
+        att = f3(1.f, 1.f, 1.f);
+        return true;
+    }
+    return false;                                                             // Emissive (materials.js:94)
+}
+
+template <bool USE_BVH, bool COUNT, bool SHADOW, bool HYBRID = true>
+__device__ __forceinline__ Hit trace(const DevScene& sc, float3 O, float3 D, float tMax, uint32_t self, Counters& cnt,
+                                     uint32_t* sstack, int sstride) {
+    if (COUNT && !SHADOW) cnt.rays++;
+    if (USE_BVH) return trace_bvh<COUNT, SHADOW, HYBRID>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride);
+    return trace_brute<COUNT, SHADOW>(sc, O, D, 0.001f, tMax, self, cnt);
+}
+
+
+}  // namespace brt
