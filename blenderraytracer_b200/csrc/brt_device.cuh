@@ -311,7 +311,7 @@ __device__ __forceinline__ Hit trace_brute(const DevScene& sc, float3 O, float3 
 // free); deeper entries (rare) spill to a per-thread local array.
 constexpr int SMEM_STACK = 12;
 constexpr int LOCAL_STACK = 52;
-constexpr int SMEM_ONLY_MAX_DEPTH = 40;   // trees up to this depth run with the whole stack in shared memory (20 KB / block at 40)
+constexpr int SMEM_ONLY_MAX_DEPTH = 32;   // trees up to this depth run with the whole stack in shared memory (16.5 KB / block at 32)
 constexpr uint32_t TRAV_DONE = 0xFFFFFFFFu;
 
 struct RayInv { float3 inv, ood; };

@@ -236,3 +236,21 @@ def test_textured_materials_render_like_the_oracle(brt):
     # the textures are really there: the checkered floor is not a flat colour
     floor = out["bvh"][H - 10:, :, 0].astype(int)
     assert floor.max() - floor.min() > 60
+
+
+def test_pathologically_deep_lbvh_uses_the_hybrid_stack(brt):
+    """Centroids at E*2^-j along each axis give Morton codes with a single set bit each: the LBVH degenerates into a chain
+    deeper than SMEM_ONLY_MAX_DEPTH (32), which selects the kernel variant whose stack spills from shared to local memory.
+    Results must not care."""
+    E = 8.0
+    objs = [dict(type="sphere", center=[E, E, E], radius=0.4, material=LAM)]
+    for j in range(1, 11):
+        for ax in range(3):
+            c = [0.0, 0.0, 0.0]
+            c[ax] = E * 2.0 ** -j
+            objs.append(dict(type="sphere", center=c, radius=0.02 + 0.01 * j, material=LAM))
+    objs += [dict(type="sphere", center=[0, 0, 0], radius=0.05 + 0.0004 * k, material=dict(type="metal", color=[0.9, 0.8, 0.7], roughness=0.1)) for k in range(120)]
+    scene = dict(objects=objs, camera=dict(position=[3, 2.5, 9], lookAt=[1.5, 1, 0], fov=55, aspect=1.5, aperture=0.0, focusDist=9.0),
+                 background=dict(type="gradient"))
+    rt, _ = _check(brt, scene, 150, 100, spp=4, depth=6, max_id_mismatch=4)
+    assert rt.sceneInfo()["bvh_depth"] > 32, rt.sceneInfo()["bvh_depth"]
