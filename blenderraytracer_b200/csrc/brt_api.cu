@@ -38,7 +38,7 @@ struct brt_ctx {
     DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm, dPrim64, dTex, dTexPerm;
     BvhWorkspace bvhWs;
     DevScene dev{};
-    bool sceneDirty = true, permDirty = true;
+    bool sceneDirty = true, permDirty = true, bvhDirty = true;
     int nBounded = 0;
     brt_scene_info info{};
     // frame buffers
@@ -300,24 +300,36 @@ static int upload_scene(brt_ctx* ctx) {
     d.lights = (const float4*)ctx->dLights.p; d.prim64 = (const double*)ctx->dPrim64.p;
     d.tex = (const float4*)ctx->dTex.p; d.texPerm = (const unsigned char*)ctx->dTexPerm.p; d.nTex = (int)s.textures.size();
     auto t1 = std::chrono::steady_clock::now();
-    // LBVH over the bounded primitives
-    d.nodes = nullptr; d.nNodes = 0;
+    // the LBVH over the bounded primitives is built on first use (ensure_bvh): tiny scenes render with the linear loop
+    d.nodes = nullptr; d.nNodes = 0; d.bvhStackDepth = 0;
     ctx->nBounded = d.nSph + d.nBox + d.nTri;
-    BvhBuildResult br{};
-    CK(build_lbvh(d, &ctx->bvhWs, &br, ctx->stream));
-    if (br.depth > SMEM_STACK + LOCAL_STACK) {
-        return fail(ctx, BRT_E_STATE, "LBVH deeper than the traversal stack (" + std::to_string(br.depth) + ")");
-    }
-    d.nodes = br.nodes; d.nNodes = (int)br.nNodes; d.bvhStackDepth = br.depth;
+    ctx->bvhDirty = true;
     brt_scene_info& inf = ctx->info;
     inf.n_objects = (int)s.objects.size(); inf.n_materials = (int)s.materials.size(); inf.n_lights = (int)s.lights.size();
     inf.n_spheres = d.nSph; inf.n_planes = d.nPln; inf.n_boxes = d.nBox; inf.n_triangles = d.nTri;
-    inf.n_bvh_nodes = br.nNodes; inf.bvh_depth = br.depth; inf.bvh_build_ms = br.buildMs;
+    inf.n_bvh_nodes = 0; inf.bvh_depth = 0; inf.bvh_build_ms = 0;
     inf.upload_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     inf.upload_bytes = (int64_t)((sph.size() + pln.size() + box.size() + tri.size() + mat.size() + lights.size()) * sizeof(float4) +
                                  meta.size() * sizeof(int4) + matType.size() * sizeof(int) + prim64.size() * sizeof(double));
     ctx->sceneDirty = false;
     return BRT_OK;
+}
+
+static int ensure_bvh(brt_ctx* ctx) {
+    if (!ctx->bvhDirty) return BRT_OK;
+    BvhBuildResult br{};
+    CK(build_lbvh(ctx->dev, &ctx->bvhWs, &br, ctx->stream));
+    if (br.depth > SMEM_STACK + LOCAL_STACK) return fail(ctx, BRT_E_STATE, "LBVH deeper than the traversal stack (" + std::to_string(br.depth) + ")");
+    ctx->dev.nodes = br.nodes; ctx->dev.nNodes = (int)br.nNodes; ctx->dev.bvhStackDepth = br.depth;
+    ctx->info.n_bvh_nodes = br.nNodes; ctx->info.bvh_depth = br.depth; ctx->info.bvh_build_ms = br.buildMs;
+    ctx->bvhDirty = false;
+    return BRT_OK;
+}
+// BRUTE reproduces the reference's loops; AUTO takes the hierarchy from 8 bounded primitives up (below that the linear loop wins)
+static bool wants_bvh(const brt_ctx* ctx) {
+    if (ctx->rp.accel == BRT_ACCEL_BRUTE) return false;
+    if (ctx->rp.accel == BRT_ACCEL_BVH) return ctx->nBounded >= 2;
+    return ctx->nBounded >= 8;
 }
 
 static int upload_perm(brt_ctx* ctx) {
@@ -348,6 +360,7 @@ int brt_scene_info_get(brt_ctx* ctx, brt_scene_info* out) {
     }
     int rc = upload_scene(ctx);
     if (rc != BRT_OK) return rc;
+    if ((rc = ensure_bvh(ctx)) != BRT_OK) return rc;               // the query reports the hierarchy, so it builds it
     *out = ctx->info;
     return BRT_OK;
 }
@@ -412,12 +425,7 @@ int brt_get_render_params(brt_ctx* ctx, brt_render_params* out) {
 }
 
 // ------------------------------------------------------------------------------------------- render
-static bool use_bvh(const brt_ctx* ctx) {
-    if (ctx->dev.nNodes == 0) return false;
-    if (ctx->rp.accel == BRT_ACCEL_BRUTE) return false;
-    if (ctx->rp.accel == BRT_ACCEL_BVH) return true;
-    return ctx->nBounded >= 8;
-}
+static bool use_bvh(const brt_ctx* ctx) { return wants_bvh(ctx) && !ctx->bvhDirty && ctx->dev.nNodes > 0; }
 static int effective_spp(const brt_render_params& rp) { return rp.aa_mode == BRT_AA_NONE ? 1 : rp.spp; }    // ray-tracer.js:201
 
 static int prepare(brt_ctx* ctx, PTParams& p) {
@@ -427,6 +435,7 @@ static int prepare(brt_ctx* ctx, PTParams& p) {
     CK(cudaSetDevice(ctx->device));
     int rc = upload_scene(ctx);
     if (rc != BRT_OK) return rc;
+    if (wants_bvh(ctx) && (rc = ensure_bvh(ctx)) != BRT_OK) return rc;
     if ((rc = upload_perm(ctx)) != BRT_OK) return rc;
     const brt_render_params& rp = ctx->rp;
     memset(&p, 0, sizeof(p));
