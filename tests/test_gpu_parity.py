@@ -548,3 +548,28 @@ def test_direct_lighting_extension_matches_oracle(brt, sample_mesh):
     rt.directLighting = False
     off = rt.render(want_linear=True)
     assert rt.linearMean[..., :3].mean() < orc.linear[..., :3].mean()      # lights add energy
+
+
+@pytest.mark.parametrize("name,W,H,depth,bound", [("sample_scene", 150, 100, 10, 0.012), ("c4_cornell", 96, 54, 16, 0.05)])
+def test_converged_images_rmse(brt, name, W, H, depth, bound):
+    """North star: "converged images are within a stated per-pixel RMSE of the reference renderer at high spp".
+    Stated bound: on tone-mapped [0,1] values, RMSE(GPU @ N spp, oracle @ N spp) at N = 1024 is <= 0.012 on the sky-lit
+    sample scene and <= 0.05 on the Cornell-style scene (small emitters, no next-event estimation in the reference: its own
+    seed-to-seed RMSE is that large), and it falls like 1/sqrt(N) — two unbiased estimators of the same image: quadrupling
+    N must at least cut the RMSE by 1.6x (2x expected) — with no per-channel bias beyond 2e-3."""
+    from oracle.oracle import OracleRayTracer
+    scene = _scenes()[name][0]
+    rmse = {}
+    for n in (64, 256, 1024):
+        rt = brt.RayTracer(W, H, seed=100 + n)
+        orc = OracleRayTracer(W, H, seed=200 + n, threads=8)
+        assert rt.loadFromJSON(scene) and orc.loadFromJSON(scene)
+        for r in (rt, orc):
+            r.updateRenderSettings(dict(samples=n, maxBounces=depth))
+        rt.render(); orc.render()
+        g, a = rt.floatData[..., :3].astype(np.float64), orc.floatData[..., :3].astype(np.float64)
+        rmse[n] = float(np.sqrt(np.mean((g - a) ** 2)))
+        bias = (g - a).mean(axis=(0, 1))
+    assert rmse[1024] <= bound, rmse
+    assert rmse[256] <= rmse[64] / 1.6 and rmse[1024] <= rmse[256] / 1.6, rmse
+    assert np.abs(bias).max() <= 2e-3, bias
