@@ -633,6 +633,13 @@ int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_me
     ctx->stats = brt_stats{};
     const int spp = effective_spp(ctx->rp);
     int batch = ctx->rp.spp_batch > 0 ? ctx->rp.spp_batch : (cb ? (spp + 15) / 16 : spp);
+    if (ctx->rp.spp_batch <= 0) {
+        // keep one launch to a few seconds at most so brt_cancel is honoured promptly (it is polled between launches):
+        // about 4e9 path samples per launch
+        long long cap = 4000000000LL / (long long)(px ? px : 1);
+        if (cap < 1) cap = 1;
+        if (batch > cap) batch = (int)cap;
+    }
     if (batch < 1) batch = 1;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int s = 0; s < spp; s += batch) {

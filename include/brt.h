@@ -58,10 +58,14 @@ enum { BRT_TONEMAP_REINHARD = 0, BRT_TONEMAP_ACES = 1, BRT_TONEMAP_LINEAR = 2 };
 /* camera.js:25 tests `type === 'perspective'`, camera.js:39 tests `type === 'orthographic'`; any other
  * string gets the un-scaled viewport with the perspective ray formula = BRT_CAM_OTHER. */
 enum { BRT_CAM_PERSPECTIVE = 0, BRT_CAM_ORTHOGRAPHIC = 1, BRT_CAM_OTHER = 2 };
-/* FAST: direct-inversion sampling, one Philox block per bounce (same distributions as math.js:22-31).
+/* FAST: direct-inversion sampling, one Philox block per bounce (same distributions as math.js:22-31); fp32 throughout.
  * REFERENCE: rejection sampling, draws consumed in the reference's exact order from the sequential
- * (seed, pixel, sample) stream — sample-for-sample comparable with the float64 oracle. */
+ * (seed, pixel, sample) stream — sample-for-sample comparable with the float64 oracle; primary rays are generated and
+ * the primary hit is evaluated in float64 (as in the AOV kernel). */
 enum { BRT_SAMPLER_FAST = 0, BRT_SAMPLER_REFERENCE = 1 };
+/* MEGAKERNEL: one thread per pixel, blocking traversal.  WAVEFRONT: persistent warp-local wavefront (path slots and ray queue
+ * in shared memory).  AUTO = MEGAKERNEL, the faster of the two on every measured configuration.  Both trace
+ * the same paths; images agree up to fp32 summation order.  count_tests renders always run the megakernel. */
 enum { BRT_INTEGRATOR_AUTO = 0, BRT_INTEGRATOR_MEGAKERNEL = 1, BRT_INTEGRATOR_WAVEFRONT = 2 };
 /* BRUTE reproduces the reference's linear loops (world.js:24-30, geometry.js:253-259); BVH must give identical results. */
 enum { BRT_ACCEL_AUTO = 0, BRT_ACCEL_BRUTE = 1, BRT_ACCEL_BVH = 2 };
@@ -146,8 +150,8 @@ typedef struct brt_render_params {
     int32_t accel;               /* BRT_ACCEL_* */
     int32_t spp_batch;           /* samples per launch between progress callbacks / cancel polls; 0 = auto */
     int32_t count_tests;         /* 1 = counting build of the same traversal (fills brt_stats.tests_*) */
-    int32_t refill_threshold;    /* tuning: idle lanes of a warp fetch the next queued ray once this many are idle; 0 = default (8) */
-    int32_t paths_in_flight;     /* tuning: samples of a pixel in flight per lane (1..4); 0 = default (2) */
+    int32_t refill_threshold;    /* WAVEFRONT tuning: idle lanes of a warp fetch the next queued ray once this many are idle; 0 = default (8) */
+    int32_t paths_in_flight;     /* WAVEFRONT tuning: samples of a pixel in flight per lane (1..4); 0 = default (2) */
     int32_t preview;             /* 1 = progressive preview: before every progress callback the image of the samples traced so far
                                     is resolved into the caller's rgba8 buffer (the reference blits finished rows, ray-tracer.js:236-238) */
     int32_t _pad1;
