@@ -9,7 +9,8 @@
 // tests, golden vectors or fixtures beyond two sample scenes, and no JS engine
 // exists in this image, so the reference itself cannot be run here.  The
 // oracle is pinned instead against hand-derived float64 known-answer vectors
-// (tests/golden/) that follow the cited formulas.
+// (tests/golden/) that follow the cited formulas, and cross-pinned bit for bit against a second,
+// independently written restatement (tests/golden/independent_port.py -> independent_vectors.npz).
 //
 // Every function cites the reference file:line it follows.  Arithmetic is
 // IEEE double with no FMA contraction (compile with -ffp-contract=off) because

@@ -252,3 +252,37 @@ def test_threads_do_not_change_the_image(sample_scene):
     assert np.array_equal(ia, ib) and np.array_equal(a.linear, b.linear)
     c = OracleRayTracer(60, 40, seed=6, threads=4); c.loadFromJSON(sample_scene)
     assert not np.array_equal(c.render(), ia)
+
+
+def test_oracle_matches_independent_port():
+    """Cross-pin: the C++ oracle against tests/golden/independent_vectors.npz — whole stochastic images produced by a second,
+    independently written restatement of the reference (tests/golden/independent_port.py, pure Python doubles) fed the same
+    Philox stream.  Linear radiance must agree bit for bit (same IEEE operations in the same order), and so must the
+    tone-mapped fp32 floatData and the RGBA8 bytes (both call the same libm for pow / tan / exp / sin)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "independent_vectors.npz"))
+    meta = json.loads(str(z["meta"]))
+    assert len(meta) >= 13
+    for case in meta:
+        name, W, H = case["name"], case["W"], case["H"]
+        rt = OracleRayTracer(W, H, seed=case["seed"], threads=2, perm_seed=case.get("perm_seed") or 0)
+        if name.startswith("preset_"):
+            rt.loadPreset(name[len("preset_"):])
+        else:
+            assert rt.loadFromJSON(case["scene"])
+        rt.updateRenderSettings(dict(samples=case["spp"], maxBounces=case["depth"], antiAliasing=case.get("aa", "supersampling"),
+                                     toneMapping=case.get("tonemap", "reinhard"), exposure=case.get("exposure", 1.0),
+                                     gamma=case.get("gamma", 2.2), denoising=case.get("denoise", False),
+                                     denoiseStrength=case.get("strength", 0.5)))
+        img = rt.render()
+        np.testing.assert_array_equal(rt.linear[..., :3], z[name + "_linear"], err_msg=name)
+        want_f = z[name + "_float"]
+        got_f = rt.denoised if case.get("denoise") else rt.floatData
+        if case.get("denoise"):
+            # the port keeps the un-denoised floatData (as ray-tracer.js does) and only the 8-bit image is replaced
+            np.testing.assert_array_equal(rt.floatData, want_f, err_msg=name)
+        else:
+            np.testing.assert_array_equal(got_f, want_f, err_msg=name)
+        np.testing.assert_array_equal(img, z[name + "_rgba"], err_msg=name)
