@@ -35,7 +35,7 @@ def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (g++ -O2 -ffp-contract=off)."""
     src = os.path.join(_HERE, "brt_oracle.cpp")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=2)       # keep our stdout clean (bench.py prints one JSON line)
     return _LIB_PATH
 
 
