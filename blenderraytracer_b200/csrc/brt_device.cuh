@@ -260,9 +260,13 @@ __device__ __forceinline__ void consider(const DevScene& sc, Hit& best, float t,
     }
 }
 
-template <bool COUNT, bool SHADOW>
+// PRIMS: compile-time mask of the bounded primitive types the BVH can hold (1 sphere | 2 box | 4 triangle; 7 = any).  A scene
+// with a single bounded type (random spheres; one big mesh) runs a kernel whose leaf code has no type dispatch at all.
+constexpr int PRIMS_ANY = 7, PRIMS_SPHERE = 1, PRIMS_BOX = 2, PRIMS_TRI = 4;
+template <bool COUNT, bool SHADOW, int PRIMS = PRIMS_ANY>
 __device__ __forceinline__ void test_prim(const DevScene& sc, uint32_t pid, float3 O, float3 D, float tMin, uint32_t self, Hit& best, Counters& cnt) {
     uint32_t ty = pid_type(pid), ix = pid_index(pid);
+    if (PRIMS == PRIMS_SPHERE) ty = PT_SPHERE; else if (PRIMS == PRIMS_TRI) ty = PT_TRI; else if (PRIMS == PRIMS_BOX) ty = PT_BOX;
     float t; int face = 0;
     bool h;
     if (ty == PT_TRI) {
@@ -354,7 +358,7 @@ __device__ __forceinline__ bool node_visit(const float4* __restrict__ nodes, uin
 // Blocking traversal: runs one ray to completion.  HYBRID = false: the whole stack lives in shared memory (the launcher
 // sized it from the tree depth: depth + 1 entries per thread) and the loop carries no local-memory path at all;
 // HYBRID = true (trees deeper than SMEM_ONLY_MAX_DEPTH): SMEM_STACK entries in shared memory, the rest in a local array.
-template <bool COUNT, bool SHADOW, bool HYBRID = true>
+template <bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY>
 __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
                                          uint32_t* sstack /* &smem[threadIdx.x] */, int sstride) {
     Hit best; best.t = tMax; best.pid = PID_NONE;
@@ -366,7 +370,7 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
     uint32_t cur = 0;
     for (;;) {
         if (cur & LEAF_BIT) {
-            test_prim<COUNT, SHADOW>(sc, cur & ~LEAF_BIT, O, D, tMin, self, best, cnt);
+            test_prim<COUNT, SHADOW, PRIMS>(sc, cur & ~LEAF_BIT, O, D, tMin, self, best, cnt);
             if (SHADOW && best.pid != PID_NONE) break;
         } else {
             if (COUNT) cnt.aabb += 2;

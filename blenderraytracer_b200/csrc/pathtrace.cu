@@ -13,7 +13,7 @@ namespace brt {
 // (profiles/): the wavefront raises SIMD efficiency of the traversal loop (15 -> 22 active lanes per instruction) but pays
 // for it in queue traffic, refill code and L1 capacity lost to shared memory; the megakernel is faster there and is what
 // BRT_INTEGRATOR_AUTO selects.  Both produce the same image up to fp32 summation order.
-template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID>
+template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID, int PRIMS = PRIMS_ANY>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega(const __grid_constant__ PTParams p) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 } else camera_ray32(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                 beta = f3(1.f, 1.f, 1.f); self = PID_NONE; depth = 0; alive = true;
             }
-            Hit h = trace<USE_BVH, COUNT, false, HYBRID>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK);
+            Hit h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK);
             if (h.pid == PID_NONE) {                                          // ray-tracer.js:122
                 sum = sum + beta * background(sc, D);
                 alive = false;
@@ -186,6 +186,10 @@ static cudaError_t launch_pt3(const PTParams& p, dim3 grid, cudaStream_t st) {
     const bool hybrid = p.sc.bvhStackDepth > SMEM_ONLY_MAX_DEPTH;
     size_t smem = (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 1) * PT_BLOCK * sizeof(uint32_t);
     if (hybrid) k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, USE_BVH><<<grid, PT_BLOCK, smem, st>>>(p);
+    else if (SAMPLER == 0 && !COUNT && !DIRECT && p.sc.nBox == 0 && p.sc.nTri == 0)      // the common hot configurations get a
+        k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, false, PRIMS_SPHERE><<<grid, PT_BLOCK, smem, st>>>(p);   // leaf test
+    else if (SAMPLER == 0 && !COUNT && !DIRECT && p.sc.nBox == 0 && p.sc.nSph == 0)      // without type dispatch
+        k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, false, PRIMS_TRI><<<grid, PT_BLOCK, smem, st>>>(p);
     else k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, false><<<grid, PT_BLOCK, smem, st>>>(p);
     return cudaGetLastError();
 }
