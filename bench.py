@@ -325,6 +325,12 @@ def run_ours(args):
                     "rays_per_sample": st["rays"] / max(1, W * H * count),
                     "tests": {k: st[k] for k in FLOPS},
                     "flops_bruteforce_per_launch": float(st["rays"]) * n_obj_flops,
+                    # SURVEY 8(d) bytes model of the traversal: 64 B per node visit, 48 / 16 / 32 B per triangle / sphere / box test,
+                    # 32 B per plane test — an UPPER bound on memory traffic (L1 / L2 serve nearly all of it; see `traffic`)
+                    "bvh_bytes_model": {"bytes_per_launch": (bvh_bytes := st["tests_aabb"] // 2 * 64 + st["tests_tri_a"] * 48 + st["tests_sphere"] * 16
+                                                             + st["tests_box"] * 32 + st["tests_plane"] * 32),
+                                        "achieved_GBps": bvh_bytes / (kern_ms_avg * 1e-3) / 1e9, "hbm_peak_GBps": hbm_peak,
+                                        "frac_of_hbm": bvh_bytes / (kern_ms_avg * 1e-3) / 1e9 / hbm_peak},
                     "note": "not a dense contraction: no tensor cores; scene + BVH are L1/L2 resident, HBM traffic is the accumulation buffer only",
                     # the same kernel against the HBM roofline, for completeness: algorithmic bytes = one read-modify-write of the
                     # W*H*16 B accumulation buffer per launch; it shows why "hbm" is not the bound of this path

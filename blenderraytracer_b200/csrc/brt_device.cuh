@@ -114,8 +114,10 @@ __device__ __forceinline__ uint4 philox_fast(uint32_t c0, uint32_t c1, uint32_t 
 // are compared with the float64 reference come from refine_primary, not from here.  -DBRT_IEEE_RCP restores __frcp_rn.
 #ifdef BRT_IEEE_RCP
 __device__ __forceinline__ float rcpf(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float sqrtfa(float x) { return sqrtf(x); }
 #else
 __device__ __forceinline__ float rcpf(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrtfa(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // same reasoning for the sphere root
 #endif
 constexpr uint32_t PHILOX_TAG = 0x42525431u;   // "BRT1"
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
@@ -155,7 +157,7 @@ __device__ __forceinline__ bool hit_sphere(float4 s, float3 O, float3 D, float t
     float3 l = madd(D, -k, oc);
     float disc = fmaf(s.w, s.w, -dot(l, l));
     if (disc < 0.f) return false;
-    float sq = sqrtf(__fmul_rn(a, disc));
+    float sq = sqrtfa(__fmul_rn(a, disc));
     float root = __fmul_rn(-hb - sq, inva);
     if (root < tMin) {
         root = __fmul_rn(sq - hb, inva);
@@ -169,7 +171,7 @@ __device__ __forceinline__ bool hit_plane(float4 n, float4 p, float3 O, float3 D
     float3 N = xyz(n);
     float denom = dot(N, D);
     if (fabsf(denom) < 1e-6f) return false;
-    float tt = __fdiv_rn(dot(xyz(p) - O, N), denom);
+    float tt = __fmul_rn(dot(xyz(p) - O, N), rcpf(denom));
     if (!(tt >= tMin)) return false;
     t = tt;
     return true;

@@ -34,10 +34,11 @@ __device__ __forceinline__ void camera_ray64(const DevCamera& c, int W, int H, i
 // fp32 form of the same ray (BRT_SAMPLER_FAST render path: jittered, lens-offset camera samples have no float64 reference
 // to match bit for bit; LLC - origin is formed in float64 on the host side of this call and rounded once).
 __device__ __forceinline__ void camera_ray32(const DevCamera& c, int W, int H, int aaMode, int col, int jUp, CamSample cs, float3& O, float3& D) {
+    const float iw = rcpf((float)W), ih = rcpf((float)H);
     float u, v;
-    if (aaMode == 1) { u = __fdiv_rn((float)col + cs.s, (float)W); v = __fdiv_rn((float)jUp + cs.t, (float)H); }
-    else if (aaMode == 2) { u = __fdiv_rn(fmaf(cs.s, 0.5f, (float)col + 0.5f), (float)W); v = __fdiv_rn(fmaf(cs.t, 0.5f, (float)jUp + 0.5f), (float)H); }
-    else { u = __fdiv_rn((float)col + 0.5f, (float)W); v = __fdiv_rn((float)jUp + 0.5f, (float)H); }
+    if (aaMode == 1) { u = __fmul_rn((float)col + cs.s, iw); v = __fmul_rn((float)jUp + cs.t, ih); }
+    else if (aaMode == 2) { u = __fmul_rn(fmaf(cs.s, 0.5f, (float)col + 0.5f), iw); v = __fmul_rn(fmaf(cs.t, 0.5f, (float)jUp + 0.5f), ih); }
+    else { u = __fmul_rn((float)col + 0.5f, iw); v = __fmul_rn((float)jUp + 0.5f, ih); }
     float rx = __fmul_rn(cs.dx, (float)c.lensRadius), ry = __fmul_rn(cs.dy, (float)c.lensRadius);
     float3 off = madd(f3((float)c.cv[0], (float)c.cv[1], (float)c.cv[2]), ry, f3((float)c.cu[0], (float)c.cu[1], (float)c.cu[2]) * rx);
     O = f3((float)c.o[0], (float)c.o[1], (float)c.o[2]) + off;
