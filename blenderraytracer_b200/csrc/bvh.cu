@@ -7,7 +7,9 @@
 // Node layout (64 B): n0 = child0 (min.x,max.x,min.y,max.y); n1 = child1 (same); n2 = (c0.min.z,c0.max.z,c1.min.z,c1.max.z);
 // n3 = (child0, child1, 0, 0) bit patterns, LEAF_BIT | pid for leaves.
 #include "brt_kernels.h"
+#include <algorithm>
 #include <cfloat>
+#include <cstring>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -15,6 +17,7 @@
 namespace brt {
 
 struct Aabb { float mn[3], mx[3]; };
+static inline float __uint_as_float_host(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 __device__ __forceinline__ Aabb prim_aabb(const DevScene& sc, uint32_t pid) {
     uint32_t ty = pid_type(pid), ix = pid_index(pid);
@@ -263,6 +266,62 @@ __global__ void __launch_bounds__(256) k_sah_cost(const Aabb* nodeBox, int nInte
     if (threadIdx.x == 0) blockSums[blockIdx.x] = red[0];
 }
 
+// ---- small scenes: a full-sweep SAH hierarchy built on the host -------------------------------------------------------
+// For up to SAH_HOST_MAX bounded primitives (a few hundred objects placed by hand or by the exporter — the reference's own
+// scale) a top-down surface-area-heuristic build over the SAME padded device AABBs costs well under a millisecond on one
+// host core and gives a markedly better tree than any Morton-order LBVH.  It is offered as a third candidate and ranked by
+// the same surface-area cost; large meshes stay with the GPU LBVH.  Same node format, same single-primitive leaves, so the
+// traversal (and therefore every result) is unchanged.
+constexpr int SAH_HOST_MAX = 16384;
+struct HostSah {
+    const std::vector<Aabb>& box; const std::vector<uint32_t>& pid;
+    std::vector<float4> nodes; std::vector<int> idx; double cost = 0.0; int depth = 0;
+    HostSah(const std::vector<Aabb>& b, const std::vector<uint32_t>& p) : box(b), pid(p) {}
+    static double area(const Aabb& b) {
+        double dx = (double)b.mx[0] - b.mn[0], dy = (double)b.mx[1] - b.mn[1], dz = (double)b.mx[2] - b.mn[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    static void grow(Aabb& a, const Aabb& b) { for (int k = 0; k < 3; k++) { a.mn[k] = std::min(a.mn[k], b.mn[k]); a.mx[k] = std::max(a.mx[k], b.mx[k]); } }
+    static Aabb empty() { Aabb e; for (int k = 0; k < 3; k++) { e.mn[k] = FLT_MAX; e.mx[k] = -FLT_MAX; } return e; }
+    // builds the subtree over idx[lo, hi) (hi - lo >= 2); returns its node index, its box in `out`, its height in `h`
+    int build(int lo, int hi, Aabb& out, int& h) {
+        const int n = hi - lo, me = (int)(nodes.size() / 4);
+        nodes.resize(nodes.size() + 4);
+        int bestAxis = 0, bestK = n / 2; double bestC = DBL_MAX;
+        std::vector<double> right(n);
+        for (int ax = 0; ax < 3; ax++) {
+            std::stable_sort(idx.begin() + lo, idx.begin() + hi, [&](int a, int b) {
+                return box[a].mn[ax] + box[a].mx[ax] < box[b].mn[ax] + box[b].mx[ax]; });
+            Aabb acc = empty();
+            for (int k = n - 1; k >= 1; k--) { grow(acc, box[idx[lo + k]]); right[k] = area(acc); }
+            acc = empty();
+            for (int k = 1; k < n; k++) {
+                grow(acc, box[idx[lo + k - 1]]);
+                double c = area(acc) * k + right[k] * (n - k);
+                // ties (identical boxes) go to the most balanced split so duplicates cannot degenerate into a chain
+                if (c < bestC || (c == bestC && std::abs(k - n / 2) < std::abs(bestK - n / 2))) { bestC = c; bestAxis = ax; bestK = k; }
+            }
+        }
+        std::stable_sort(idx.begin() + lo, idx.begin() + hi, [&](int a, int b) {
+            return box[a].mn[bestAxis] + box[a].mx[bestAxis] < box[b].mn[bestAxis] + box[b].mx[bestAxis]; });
+        Aabb cb[2]; uint32_t ref[2]; int ch[2] = { 0, 0 };
+        const int range[2][2] = { { lo, lo + bestK }, { lo + bestK, hi } };
+        for (int c = 0; c < 2; c++) {
+            if (range[c][1] - range[c][0] == 1) { int pi = idx[range[c][0]]; cb[c] = box[pi]; ref[c] = LEAF_BIT | pid[pi]; }
+            else { ref[c] = (uint32_t)build(range[c][0], range[c][1], cb[c], ch[c]); }
+        }
+        float4* np = &nodes[4 * (size_t)me];
+        np[0] = make_float4(cb[0].mn[0], cb[0].mx[0], cb[0].mn[1], cb[0].mx[1]);
+        np[1] = make_float4(cb[1].mn[0], cb[1].mx[0], cb[1].mn[1], cb[1].mx[1]);
+        np[2] = make_float4(cb[0].mn[2], cb[0].mx[2], cb[1].mn[2], cb[1].mx[2]);
+        np[3] = make_float4(__uint_as_float_host(ref[0]), __uint_as_float_host(ref[1]), 0.f, 0.f);
+        out = cb[0]; grow(out, cb[1]);
+        cost += area(out);
+        h = 1 + std::max(ch[0], ch[1]);
+        return me;
+    }
+};
+
 #define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return e_; } } while (0)
 
 void free_bvh_workspace(BvhWorkspace* ws) {
@@ -345,6 +404,29 @@ cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out
         if (bestMode < 0 || cost < 0.9 * bestCost) { bestCost = cost; bestMode = mode; bestDepth = depth; }
     }
     if (bestMode == 1) nodes = nodesAlt;
+    if (n <= SAH_HOST_MAX) {
+        // third candidate: host SAH over the padded device boxes (written into the node buffer the LBVH choice did not take)
+        std::vector<Aabb> hb(n);
+        BVH_CK(cudaMemcpyAsync(hb.data(), boxes, sizeof(Aabb) * n, cudaMemcpyDeviceToHost, st));
+        BVH_CK(cudaStreamSynchronize(st));
+        std::vector<uint32_t> pids(n);
+        for (int i = 0; i < n; i++) pids[i] = i < sc.nSph ? make_pid(PT_SPHERE, i) : i < sc.nSph + sc.nBox ? make_pid(PT_BOX, i - sc.nSph) : make_pid(PT_TRI, i - sc.nSph - sc.nBox);
+        HostSah sah(hb, pids);
+        sah.idx.resize(n);
+        for (int i = 0; i < n; i++) sah.idx[i] = i;
+        sah.nodes.reserve(4 * (size_t)(n - 1));
+        Aabb rootBox; int height = 0;
+        sah.build(0, n, rootBox, height);
+        if (getenv("BRT_DEBUG")) fprintf(stderr, "[brt] host sah candidate: sah cost %.6g depth %d\n", sah.cost, height);
+        const char* mg = getenv("BRT_SAH_MARGIN");
+        const double margin = mg ? atof(mg) : 0.9;
+        if (sah.cost < margin * bestCost && height <= SMEM_ONLY_MAX_DEPTH) {
+            float4* target = nodes == ws->nodes[0] ? ws->nodes[1] : ws->nodes[0];
+            BVH_CK(cudaMemcpyAsync(target, sah.nodes.data(), sizeof(float4) * sah.nodes.size(), cudaMemcpyHostToDevice, st));
+            BVH_CK(cudaStreamSynchronize(st));
+            nodes = target; bestCost = sah.cost; bestDepth = height; bestMode = 2;
+        }
+    }
     BVH_CK(cudaEventRecord(e1, st));
     BVH_CK(cudaGetLastError());
     BVH_CK(cudaEventSynchronize(e1));
