@@ -149,7 +149,7 @@ def oracle_rate(w, threads: int, budget_s: float, spp: int = 1):
                   f"= {done} path samples, {t_used:.1f} s on {threads} thread(s)")
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -174,7 +174,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    out.append(json.dumps(line))
     return 0
 
 
@@ -183,7 +183,7 @@ def algorithmic_flops(stats: dict) -> float:
     return float(sum(stats[k] * f for k, f in FLOPS.items()))
 
 
-def run_ours(args):
+def run_ours(args, out):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -374,7 +374,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        out.append(json.dumps(line))
     return 0
 
 
@@ -415,14 +415,25 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                       # timing rule: W >= 3
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "ours":
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_ours(args)
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner, make) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    line_holder = []
+    try:
+        rc = run_reference(args, line_holder) if args.impl == "reference" else run_ours(args, line_holder)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in line_holder:
+        print(line, flush=True)
+    return rc
 
 
 if __name__ == "__main__":
