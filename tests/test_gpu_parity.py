@@ -573,3 +573,55 @@ def test_converged_images_rmse(brt, name, W, H, depth, bound):
     assert rmse[1024] <= bound, rmse
     assert rmse[256] <= rmse[64] / 1.6 and rmse[1024] <= rmse[256] / 1.6, rmse
     assert np.abs(bias).max() <= 2e-3, bias
+
+
+def test_full_size_c3_crop_statistical_parity(brt):
+    """BASELINE config 3 at its full 1920x1080 (thin lens, aperture 0.1): a crop of the frame rendered by the oracle at 64 spp
+    against the same crop of the GPU's full frame — RMSE within 1.5x the oracle's own seed-to-seed RMSE, no bias."""
+    from oracle.oracle import OracleRayTracer
+    from tools import gen_scenes
+    scene = gen_scenes.random_spheres()
+    W, H, spp = 1920, 1080, 64
+    x0, y0, x1, y1 = 864, 560, 1056, 668                  # 192 x 108 px around the three big spheres
+    rt = brt.RayTracer(W, H, seed=41)
+    assert rt.loadFromJSON(scene)
+    rt.updateRenderSettings(dict(samples=spp, maxBounces=10))
+    rt.render()
+    g = rt.floatData[y0:y1, x0:x1, :3].astype(np.float64)
+    crops = []
+    for seed in (42, 43):
+        o = OracleRayTracer(W, H, seed=seed, threads=8)
+        assert o.loadFromJSON(scene)
+        o.updateRenderSettings(dict(samples=spp, maxBounces=10))
+        o.render(rect=(x0, y0, x1, y1))
+        crops.append(o.floatData[y0:y1, x0:x1, :3].astype(np.float64))
+    a, b = crops
+    rmse, floor = np.sqrt(np.mean((g - a) ** 2)), np.sqrt(np.mean((b - a) ** 2))
+    assert rmse <= 1.5 * floor + 1e-4, (rmse, floor)
+    assert np.abs((g - a).mean(axis=(0, 1))).max() <= 2e-3 + 3 * np.abs((b - a).mean(axis=(0, 1))).max()
+    assert a.std() > 0.05                                 # the crop really contains geometry, not just sky
+
+
+def test_full_size_c5_crop_sample_for_sample(brt):
+    """BASELINE config 5 (1,002,528-triangle terrain) at its full 3840x2160: with the sequential sampler every GPU path is
+    the oracle's path, so a small crop traced by the oracle — brute force over a million triangles per ray, all bounces —
+    must match the GPU's LBVH-traversed frame pixel for pixel (within 2 LSB, barring fp32 flips)."""
+    from oracle.oracle import OracleRayTracer
+    from tools import gen_scenes, scene_binary
+    scene = gen_scenes.terrain()
+    W, H, spp = 3840, 2160, 2
+    x0, y0, x1, y1 = 1900, 1400, 1924, 1412               # 24 x 12 px on the terrain
+    rt = brt.RayTracer(W, H, seed=17)
+    assert rt.loadFromJSON(scene_binary.pack(scene))
+    rt.updateRenderSettings(dict(samples=spp, maxBounces=4))
+    rt.sampler = "reference"
+    img = rt.render(want_linear=True)
+    o = OracleRayTracer(W, H, seed=17, threads=8)
+    assert o.loadFromJSON(scene)
+    o.updateRenderSettings(dict(samples=spp, maxBounces=4))
+    ref = o.render(rect=(x0, y0, x1, y1))
+    d = np.abs(img[y0:y1, x0:x1, :3].astype(int) - ref[y0:y1, x0:x1, :3].astype(int)).max(axis=-1)
+    assert (d <= 2).mean() >= 0.95, (d <= 2).mean()
+    lin_err = np.abs(rt.linearMean[y0:y1, x0:x1, :3] - o.linear[y0:y1, x0:x1, :3])
+    assert np.median(lin_err) <= 1e-5
+    assert ref[y0:y1, x0:x1, :3].std() > 1                # terrain, not a flat sky
