@@ -9,7 +9,7 @@ namespace brt {
 constexpr int PT_BLOCK = 128;
 constexpr int PT_MIN_BLOCKS = 6;      // __launch_bounds__ min blocks/SM of the wavefront kernel (<= 80 registers)
 #ifndef PT_MIN_BLOCKS_MEGA
-#define PT_MIN_BLOCKS_MEGA 6          // megakernel: <= 80 registers; the fp32 (fast-sampler) instantiation needs 71, no spills; measured best of 5..8
+#define PT_MIN_BLOCKS_MEGA 8          // megakernel at 64 registers: 8 blocks = 32 warps / SM (measured 5..8: 8 best; 32 B of spills in the fast-sampler kernels)
 #endif
 constexpr int PT_SLOT_WORDS = 13;    // shared-memory words per path slot (pathtrace.cu: SlotField; +1 for the sequential sampler)
 
