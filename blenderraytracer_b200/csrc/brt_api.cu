@@ -449,6 +449,13 @@ static int prepare(brt_ctx* ctx, PTParams& p) {
         dc.cu[k] = c.u[k]; dc.cv[k] = c.v[k]; dc.cw[k] = c.w[k];
     }
     dc.lensRadius = c.lens_radius; dc.type = c.type;
+    DevCamera32& d32 = p.cam32;
+    for (int k = 0; k < 3; k++) {
+        d32.o[k] = (float)c.origin[k]; d32.llo[k] = (float)(c.lower_left_corner[k] - c.origin[k]);
+        d32.h[k] = (float)c.horizontal[k]; d32.v[k] = (float)c.vertical[k];
+        d32.cu[k] = (float)c.u[k]; d32.cv[k] = (float)c.v[k]; d32.cw[k] = (float)c.w[k];
+    }
+    d32.lensRadius = (float)c.lens_radius; d32.type = c.type;
     p.W = rp.width; p.H = rp.height; p.maxDepth = rp.max_depth; p.aaMode = rp.aa_mode;
     p.seedLo = (uint32_t)rp.seed; p.seedHi = (uint32_t)(rp.seed >> 32);
     p.directLighting = rp.direct_lighting ? 1 : 0;

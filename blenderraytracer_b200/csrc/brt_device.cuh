@@ -53,6 +53,13 @@ struct DevCamera {         // camera.js:14-35, derived on the host, kept in floa
     int type;
 };
 
+struct DevCamera32 {       // the same camera rounded once on the host for the fp32 (fast-sampler) ray generator;
+    float o[3], llo[3];    // llo = lowerLeftCorner - origin, formed in float64 before rounding
+    float h[3], v[3], cu[3], cv[3], cw[3];
+    float lensRadius;
+    int type;
+};
+
 struct Counters {          // counting build
     unsigned long long rays, sph, pln, box, triA, triB, triC, aabb;
 };

@@ -16,6 +16,7 @@ constexpr int PT_SLOT_WORDS = 13;    // shared-memory words per path slot (patht
 struct PTParams {
     DevScene sc;
     DevCamera cam;
+    DevCamera32 cam32;
     int W, H;
     int sBegin, sCount;          // global sample indices [sBegin, sBegin + sCount) for every pixel
     int maxDepth;

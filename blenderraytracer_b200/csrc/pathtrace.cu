@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                     D3 O64, D64;
                     camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
                     O = tof3(O64); D = tof3(D64);
-                } else camera_ray32(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
+                } else camera_ray32(p.cam32, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                 beta = f3(1.f, 1.f, 1.f); self = PID_NONE; depth = 0; alive = true;
             }
             Hit h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK);

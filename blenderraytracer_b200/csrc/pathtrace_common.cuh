@@ -33,19 +33,18 @@ __device__ __forceinline__ void camera_ray64(const DevCamera& c, int W, int H, i
 
 // fp32 form of the same ray (BRT_SAMPLER_FAST render path: jittered, lens-offset camera samples have no float64 reference
 // to match bit for bit; LLC - origin is formed in float64 on the host side of this call and rounded once).
-__device__ __forceinline__ void camera_ray32(const DevCamera& c, int W, int H, int aaMode, int col, int jUp, CamSample cs, float3& O, float3& D) {
+__device__ __forceinline__ void camera_ray32(const DevCamera32& c, int W, int H, int aaMode, int col, int jUp, CamSample cs, float3& O, float3& D) {
     const float iw = rcpf((float)W), ih = rcpf((float)H);
     float u, v;
     if (aaMode == 1) { u = __fmul_rn((float)col + cs.s, iw); v = __fmul_rn((float)jUp + cs.t, ih); }
     else if (aaMode == 2) { u = __fmul_rn(fmaf(cs.s, 0.5f, (float)col + 0.5f), iw); v = __fmul_rn(fmaf(cs.t, 0.5f, (float)jUp + 0.5f), ih); }
     else { u = __fmul_rn((float)col + 0.5f, iw); v = __fmul_rn((float)jUp + 0.5f, ih); }
-    float rx = __fmul_rn(cs.dx, (float)c.lensRadius), ry = __fmul_rn(cs.dy, (float)c.lensRadius);
-    float3 off = madd(f3((float)c.cv[0], (float)c.cv[1], (float)c.cv[2]), ry, f3((float)c.cu[0], (float)c.cu[1], (float)c.cu[2]) * rx);
-    O = f3((float)c.o[0], (float)c.o[1], (float)c.o[2]) + off;
+    float rx = __fmul_rn(cs.dx, c.lensRadius), ry = __fmul_rn(cs.dy, c.lensRadius);
+    float3 off = madd(f3(c.cv[0], c.cv[1], c.cv[2]), ry, f3(c.cu[0], c.cu[1], c.cu[2]) * rx);
+    O = f3(c.o[0], c.o[1], c.o[2]) + off;
     // D = (LLC - origin) + u*H + v*V - off
-    float3 llo = f3((float)(c.ll[0] - c.o[0]), (float)(c.ll[1] - c.o[1]), (float)(c.ll[2] - c.o[2]));
-    D = madd(f3((float)c.v[0], (float)c.v[1], (float)c.v[2]), v, madd(f3((float)c.h[0], (float)c.h[1], (float)c.h[2]), u, llo)) - off;
-    if (c.type == 1) D = normalize0(D - f3((float)c.cw[0], (float)c.cw[1], (float)c.cw[2]));
+    D = madd(f3(c.v[0], c.v[1], c.v[2]), v, madd(f3(c.h[0], c.h[1], c.h[2]), u, f3(c.llo[0], c.llo[1], c.llo[2]))) - off;
+    if (c.type == 1) D = normalize0(D - f3(c.cw[0], c.cw[1], c.cw[2]));
 }
 
 template <int SAMPLER>

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
                         D3 O64, D64;
                         camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
                         O = tof3(O64); D = tof3(D64);
-                    } else camera_ray32(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
+                    } else camera_ray32(p.cam32, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                     SLOT_F(F_OX, slot) = O.x; SLOT_F(F_OY, slot) = O.y; SLOT_F(F_OZ, slot) = O.z;
                     SLOT_F(F_DX, slot) = D.x; SLOT_F(F_DY, slot) = D.y; SLOT_F(F_DZ, slot) = D.z;
                     SLOT_F(F_BX, slot) = 1.f; SLOT_F(F_BY, slot) = 1.f; SLOT_F(F_BZ, slot) = 1.f;
