@@ -79,7 +79,10 @@ class brt_stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64),
                 ("tests_sphere", C.c_uint64), ("tests_plane", C.c_uint64), ("tests_box", C.c_uint64),
                 ("tests_tri_a", C.c_uint64), ("tests_tri_b", C.c_uint64), ("tests_tri_c", C.c_uint64), ("tests_aabb", C.c_uint64),
-                ("kernel_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_uint64)]
+                ("kernel_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_uint64),
+                ("trav_warp_iters", C.c_uint64), ("trav_lane_iters", C.c_uint64), ("trav_alive_lanes", C.c_uint64),
+                ("trav_node_issues", C.c_uint64), ("trav_leaf_issues", C.c_uint64), ("trav_leaf_lanes", C.c_uint64),
+                ("path_warp_iters", C.c_uint64), ("path_lane_iters", C.c_uint64)]
 
 
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_double, C.c_void_p)

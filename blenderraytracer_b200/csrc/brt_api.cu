@@ -140,7 +140,8 @@ static int validate_scene(brt_ctx* ctx, const HostScene& s) {
         if (o.type < BRT_OBJ_SPHERE || o.type > BRT_OBJ_MESH) return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": bad type");
         if (o.material < 0 || (size_t)o.material >= s.materials.size()) return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": bad material index");
         if (o.type == BRT_OBJ_MESH) {
-            if (o.first_tri < 0 || o.tri_count < 0 || (size_t)(o.first_tri + o.tri_count) * 9 > s.meshTris.size())
+            const uint64_t nT = s.meshTris.size() / 9;              // no arithmetic on the untrusted values: nothing can wrap
+            if (o.first_tri < 0 || o.tri_count < 0 || (uint64_t)o.first_tri > nT || (uint64_t)o.tri_count > nT - (uint64_t)o.first_tri)
                 return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": mesh triangle range out of bounds");
         }
     }
@@ -480,10 +481,9 @@ static int launch_samples(brt_ctx* ctx, PTParams& p, float* dAccum, int sBegin, 
     p.accum = (float4*)dAccum; p.sBegin = sBegin; p.sCount = sCount;
     const bool count = ctx->rp.count_tests != 0;
     if (count) {
-        CK(ctx->dCounters.ensure(8 * sizeof(unsigned long long)));
+        CK(ctx->dCounters.ensure(N_COUNTERS * sizeof(unsigned long long)));
         p.counters = (unsigned long long*)ctx->dCounters.p;
     }
-    if (p.maxDepth <= 0) return BRT_OK;                             // rayColor(depth <= 0) is black (ray-tracer.js:103)
     const int z = z_split(ctx, sCount);
     if (z > 1) {
         // small image: split the samples over z chunks to fill the GPU; every chunk accumulates into its own zeroed plane
@@ -515,6 +515,8 @@ static PostParams post_params(const brt_ctx* ctx) {
 int brt_render_accumulate(brt_ctx* ctx, float* d_accum, int sample_begin, int sample_count) {
     if (!ctx) return BRT_E_INVALID;
     if (sample_begin < 0 || sample_count < 0) return fail(ctx, BRT_E_INVALID, "negative sample range");
+    // sample indices are Philox counter words and (wavefront) packed into 24 bits of the slot state
+    if ((long long)sample_begin + sample_count > (1LL << 24)) return fail(ctx, BRT_E_INVALID, "sample_begin + sample_count must be <= 2^24");
     PTParams p;
     int rc = prepare(ctx, p);
     if (rc != BRT_OK) return rc;
@@ -525,7 +527,7 @@ int brt_render_accumulate(brt_ctx* ctx, float* d_accum, int sample_begin, int sa
         if (fresh) CK(cudaMemsetAsync(ctx->dAccum.p, 0, px * 16, ctx->stream));
         d_accum = (float*)ctx->dAccum.p;
     }
-    if (ctx->rp.count_tests) { CK(ctx->dCounters.ensure(64)); CK(cudaMemsetAsync(ctx->dCounters.p, 0, 64, ctx->stream)); }
+    if (ctx->rp.count_tests) { CK(ctx->dCounters.ensure(N_COUNTERS * 8)); CK(cudaMemsetAsync(ctx->dCounters.p, 0, N_COUNTERS * 8, ctx->stream)); }
     ctx->stats.launches = 0;
     if (sample_count == 0) return BRT_OK;
     if ((rc = launch_samples(ctx, p, d_accum, sample_begin, sample_count)) != BRT_OK) return rc;
@@ -636,7 +638,7 @@ int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_me
     if (float_data || ctx->rp.denoise) CK(ctx->dFloat.ensure(px * 16));
     if (linear_mean) CK(ctx->dLinear.ensure(px * 16));
     CK(cudaMemsetAsync(ctx->dAccum.p, 0, px * 16, ctx->stream));
-    if (ctx->rp.count_tests) { CK(ctx->dCounters.ensure(64)); CK(cudaMemsetAsync(ctx->dCounters.p, 0, 64, ctx->stream)); }
+    if (ctx->rp.count_tests) { CK(ctx->dCounters.ensure(N_COUNTERS * 8)); CK(cudaMemsetAsync(ctx->dCounters.p, 0, N_COUNTERS * 8, ctx->stream)); }
     ctx->stats = brt_stats{};
     const int spp = effective_spp(ctx->rp);
     int batch = ctx->rp.spp_batch > 0 ? ctx->rp.spp_batch : (cb ? (spp + 15) / 16 : spp);
@@ -657,7 +659,7 @@ int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_me
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->cancel.load()) return fail(ctx, BRT_E_CANCELLED, "render cancelled");
             if (cb && s + n < spp) {
-                if (ctx->rp.preview && p.maxDepth > 0) {
+                if (ctx->rp.preview) {
                     // progressive preview: the sums so far divided by their own sample count (alpha) are a complete image
                     bool dn = ctx->rp.denoise != 0;
                     if (dn) CK(ctx->dFloat.ensure(px * 16));
@@ -671,13 +673,6 @@ int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_me
         }
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (p.maxDepth <= 0) {
-        // every path is black; alpha must still carry the sample count for the resolve division
-        std::vector<float> z(px * 4, 0.f);
-        for (size_t i = 0; i < px; i++) z[4 * i + 3] = (float)spp;
-        CK(cudaMemcpyAsync(ctx->dAccum.p, z.data(), px * 16, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
     rc = brt_resolve_device(ctx, (const float*)ctx->dAccum.p, (uint8_t*)ctx->dRgba.p, (float_data || ctx->rp.denoise) ? (float*)ctx->dFloat.p : nullptr,
                             linear_mean ? (float*)ctx->dLinear.p : nullptr);
     if (rc != BRT_OK) return rc;
@@ -702,11 +697,14 @@ int brt_get_stats(brt_ctx* ctx, brt_stats* out) {
     if (!ctx || !out) return BRT_E_INVALID;
     if (ctx->device >= 0 && ctx->rp.count_tests && ctx->dCounters.p) {
         CK(cudaSetDevice(ctx->device));
-        unsigned long long c[8];
+        unsigned long long c[N_COUNTERS];
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaMemcpy(c, ctx->dCounters.p, sizeof(c), cudaMemcpyDeviceToHost));
         ctx->stats.rays = c[0]; ctx->stats.tests_sphere = c[1]; ctx->stats.tests_plane = c[2]; ctx->stats.tests_box = c[3];
         ctx->stats.tests_tri_a = c[4]; ctx->stats.tests_tri_b = c[5]; ctx->stats.tests_tri_c = c[6]; ctx->stats.tests_aabb = c[7];
+        ctx->stats.trav_warp_iters = c[8]; ctx->stats.trav_lane_iters = c[9]; ctx->stats.trav_alive_lanes = c[10];
+        ctx->stats.trav_node_issues = c[11]; ctx->stats.trav_leaf_issues = c[12]; ctx->stats.trav_leaf_lanes = c[13];
+        ctx->stats.path_warp_iters = c[14]; ctx->stats.path_lane_iters = c[15];
     }
     *out = ctx->stats;
     return BRT_OK;

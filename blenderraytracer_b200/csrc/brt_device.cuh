@@ -62,7 +62,17 @@ struct DevCamera32 {       // the same camera rounded once on the host for the f
 
 struct Counters {          // counting build
     unsigned long long rays, sph, pln, box, triA, triB, triC, aabb;
+    // SIMD-lane attribution of the BVH loop (one count per WARP iteration, taken by the lowest active lane):
+    unsigned long long trIter;       // warp-level iterations of the traversal loop
+    unsigned long long trLanes;      // lanes that executed them (sum of popc(active mask))
+    unsigned long long trAlive;      // lanes of the warp that still had samples to trace at that time (32 - drained)
+    unsigned long long trNodeIssue;  // warp iterations in which >= 1 lane visited an internal node
+    unsigned long long trLeafIssue;  // warp iterations in which >= 1 lane tested a leaf primitive
+    unsigned long long trLeafLanes;  // lanes that tested a leaf primitive
+    unsigned long long mainIter;     // warp-level iterations of the path loop (one trace call each)
+    unsigned long long mainLanes;    // lanes that executed them
 };
+constexpr int N_COUNTERS = sizeof(Counters) / sizeof(unsigned long long);
 
 // ------------------------------------------------------------------------------------------- float3 helpers
 // Every operation is spelled with an explicit rounding intrinsic (or an explicit fmaf), so nvcc's context-dependent
@@ -328,9 +338,15 @@ constexpr int SMEM_ONLY_MAX_DEPTH = 32;   // trees up to this depth run with the
 constexpr uint32_t TRAV_DONE = 0xFFFFFFFFu;
 
 struct RayInv { float3 inv, ood; };
+// A direction component that is exactly 0 (axis-parallel camera rays through the centre row / column, mirror bounces off
+// axis-aligned faces) or denormal would make inv = +-inf and `bound*inv - ood` = inf - inf = NaN on a slab that straddles the
+// origin's coordinate, which fminf / fmaxf then silently drop: the child would be culled although the origin lies inside the
+// slab.  Clamping |d| to 2^-80 keeps every slab value finite with the right sign (Aila-Laine); the primitive tests do not use
+// this reciprocal, so brute force and BVH still see the same hits.
+__device__ __forceinline__ float slab_dir(float d) { return fabsf(d) > 8.271806125530277e-25f ? d : copysignf(8.271806125530277e-25f, d); }
 __device__ __forceinline__ RayInv ray_inv(float3 O, float3 D) {
     RayInv r;
-    r.inv = f3(rcpf(D.x), rcpf(D.y), rcpf(D.z));
+    r.inv = f3(rcpf(slab_dir(D.x)), rcpf(slab_dir(D.y)), rcpf(slab_dir(D.z)));
     r.ood = O * r.inv;
     return r;
 }
@@ -369,7 +385,7 @@ __device__ __forceinline__ bool node_visit(const float4* __restrict__ nodes, uin
 // HYBRID = true (trees deeper than SMEM_ONLY_MAX_DEPTH): SMEM_STACK entries in shared memory, the rest in a local array.
 template <bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY>
 __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
-                                         uint32_t* sstack /* &smem[threadIdx.x] */, int sstride) {
+                                         uint32_t* sstack /* &smem[threadIdx.x] */, int sstride, unsigned aliveMask = 0xffffffffu) {
     Hit best; best.t = tMax; best.pid = PID_NONE;
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
     if (sc.nNodes == 0) return best;
@@ -378,6 +394,15 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
     int sp = 0;
     uint32_t cur = 0;
     for (;;) {
+        if (COUNT && !SHADOW) {
+            // lane attribution: which lanes of the warp execute this iteration, and doing what (profiles/*lane_attribution*)
+            const unsigned act = __activemask();
+            const unsigned leafM = __ballot_sync(act, (cur & LEAF_BIT) != 0u);
+            if ((int)(threadIdx.x & 31u) == __ffs(act) - 1) {
+                cnt.trIter++; cnt.trLanes += __popc(act); cnt.trAlive += __popc(aliveMask);
+                cnt.trLeafIssue += leafM ? 1 : 0; cnt.trNodeIssue += (leafM != act) ? 1 : 0; cnt.trLeafLanes += __popc(leafM);
+            }
+        }
         if (cur & LEAF_BIT) {
             test_prim<COUNT, SHADOW, PRIMS>(sc, cur & ~LEAF_BIT, O, D, tMin, self, best, cnt);
             if (SHADOW && best.pid != PID_NONE) break;

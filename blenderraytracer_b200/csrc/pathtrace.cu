@@ -13,6 +13,11 @@ namespace brt {
 // (profiles/): the wavefront raises SIMD efficiency of the traversal loop (15 -> 22 active lanes per instruction) but pays
 // for it in queue traffic, refill code and L1 capacity lost to shared memory; the megakernel is faster there and is what
 // BRT_INTEGRATOR_AUTO selects.  Both produce the same image up to fp32 summation order.
+// Lane attribution (COUNT build, profiles/r02_lane_attribution_*.md): of the 32 lane slots of a BVH-loop iteration on C3 at
+// 256 spp, 58 % work, 35 % wait for the slowest ray of the warp and 7 % are drained (their pixel has no samples left).  A
+// variant that dealt each tile's samples to the 32 lanes in balanced runs (lane L traces run r of pixel (L + r) mod 32,
+// order-independent fixed-point tile sums in shared memory) cut the drained share only to 6 % — what remains is the random
+// spread of 256-sample sums, not a systematic difference between pixels — and lost 2 % to its bookkeeping; it was removed.
 template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID, int PRIMS = PRIMS_ANY>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega(const __grid_constant__ PTParams p) {
     extern __shared__ uint32_t smem[];
@@ -43,6 +48,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
         CamSample cam = {};
         RngSeq rng;
         uint32_t* sstack = smem + threadIdx.x;
+        if (p.maxDepth <= 0) s = sEnd;                                        // rayColor(depth <= 0) is black (ray-tracer.js:103): only alpha moves
         for (;;) {
             if (!alive) {
                 if (s >= sEnd) break;
@@ -55,7 +61,12 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 } else camera_ray32(p.cam32, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                 beta = f3(1.f, 1.f, 1.f); self = PID_NONE; depth = 0; alive = true;
             }
-            Hit h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK);
+            unsigned aliveMask = 0xffffffffu;
+            if (COUNT) {
+                aliveMask = __activemask();
+                if (lane == __ffs(aliveMask) - 1) { cnt.mainIter++; cnt.mainLanes += __popc(aliveMask); }
+            }
+            Hit h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
             if (h.pid == PID_NONE) {                                          // ray-tracer.js:122
                 sum = sum + beta * background(sc, D);
                 alive = false;
@@ -105,7 +116,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
     if (COUNT) {
         unsigned long long* v = reinterpret_cast<unsigned long long*>(&cnt);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < N_COUNTERS; k++) {
             unsigned long long x = v[k];
             for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
             if (lane == 0 && x) atomicAdd(p.counters + k, x);
@@ -204,7 +215,7 @@ static cudaError_t launch_pt1(const PTParams& p, bool bvh, bool count, dim3 grid
 }
 
 cudaError_t launch_pathtrace(const PTParams& p, int sampler, bool useBvh, bool count, int zSplit, cudaStream_t st) {
-    if (p.wavefront && !count) return launch_pathtrace_wave(p, sampler, useBvh, zSplit, st);
+    if (p.wavefront && !count && p.maxDepth > 0) return launch_pathtrace_wave(p, sampler, useBvh, zSplit, st);
     dim3 grid((p.W + 15) / 16, (p.H + 7) / 8, zSplit < 1 ? 1 : zSplit);
     return sampler == 1 ? launch_pt1<1>(p, useBvh, count, grid, st) : launch_pt1<0>(p, useBvh, count, grid, st);
 }

@@ -130,9 +130,9 @@ __device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m
 
 template <bool USE_BVH, bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY>
 __device__ __forceinline__ Hit trace(const DevScene& sc, float3 O, float3 D, float tMax, uint32_t self, Counters& cnt,
-                                     uint32_t* sstack, int sstride) {
+                                     uint32_t* sstack, int sstride, unsigned aliveMask = 0xffffffffu) {
     if (COUNT && !SHADOW) cnt.rays++;
-    if (USE_BVH) return trace_bvh<COUNT, SHADOW, HYBRID, PRIMS>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride);
+    if (USE_BVH) return trace_bvh<COUNT, SHADOW, HYBRID, PRIMS>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride, aliveMask);
     return trace_brute<COUNT, SHADOW>(sc, O, D, 0.001f, tMax, self, cnt);
 }
 

@@ -178,6 +178,12 @@ typedef struct brt_stats {
     double post_ms;              /* resolve (+ denoise) */
     double total_ms;             /* brt_render wall time incl. copies */
     uint64_t launches;           /* kernels launched by the last call */
+    /* SIMD-lane attribution of the megakernel (count_tests only; one count per WARP iteration of the loop named):
+     * 32*trav_warp_iters lane slots = trav_lane_iters working + (trav_alive_lanes - trav_lane_iters) waiting for the slowest
+     * ray of the warp + (32*trav_warp_iters - trav_alive_lanes) drained (no samples left for that lane). */
+    uint64_t trav_warp_iters, trav_lane_iters, trav_alive_lanes;
+    uint64_t trav_node_issues, trav_leaf_issues, trav_leaf_lanes;   /* warp iterations with >= 1 lane at a node / at a leaf; lanes at a leaf */
+    uint64_t path_warp_iters, path_lane_iters;                       /* the path loop (one trace call per iteration) */
 } brt_stats;
 
 typedef void (*brt_progress_cb)(double fraction, void* user);   /* onProgress (ray-tracer.js:258-259,279) */

@@ -88,6 +88,35 @@ def test_axis_parallel_rays_and_box_faces(brt):
     _check(brt, scene, 101, 101, max_id_mismatch=8)
 
 
+def test_axis_parallel_rays_off_origin_bvh_equals_brute(brt):
+    """Camera (0.3, 1, 5) -> (0.3, 1, 0): the centre column has D.x == 0 and the centre row D.y == 0 with an origin that is
+    NOT on a slab plane, so `bound*inv - O*inv` would be inf - inf = NaN for every BVH box straddling x = 0.3 / y = 1 and
+    the hierarchy would lose primitives the linear loop hits.  The slab reciprocal clamps |d| >= 2^-80 instead."""
+    objs = []
+    for k in range(6):                                                      # 12 bounded primitives straddling x = 0.3 and / or y = 1
+        objs.append(dict(type="sphere", center=[0.3 + 0.05 * (k - 2.5), 1.0 + 0.45 * (k - 2.5), -1.0 - 0.3 * k], radius=0.4, material=LAM))
+        objs.append(dict(type="box", min=[-2.5 + 0.9 * k, 0.8, -3.0], max=[-1.9 + 0.9 * k, 1.2, -2.6], material=LAM))
+    objs.append(dict(type="plane", point=[0, -1, 0], normal=[0, 1, 0], material=LAM))
+    scene = dict(objects=objs, camera=dict(position=[0.3, 1, 5], lookAt=[0.3, 1, 0], fov=40, aspect=1.0, aperture=0.0, focusDist=5.0),
+                 background=dict(type="gradient"))
+    W = H = 101
+    rt = brt.RayTracer(W, H, seed=5)
+    assert rt.loadFromJSON(scene)
+    rt.updateRenderSettings(dict(samples=1, maxBounces=4, antiAliasing="none"))
+    out = {}
+    for accel in ("brute", "bvh"):
+        rt.accel = accel
+        out[accel] = (rt.primaryAOV(32), rt.render(want_linear=True).copy(), rt.linearMean.copy())
+    assert rt.sceneInfo()["n_bvh_nodes"] == 11
+    for key in ("obj_id", "tri_id", "t", "normal", "front_face"):
+        assert np.array_equal(out["brute"][0][key], out["bvh"][0][key]), key
+    assert np.array_equal(out["brute"][1], out["bvh"][1])
+    assert np.array_equal(out["brute"][2], out["bvh"][2])
+    col, row = out["bvh"][0]["obj_id"][:, W // 2], out["bvh"][0]["obj_id"][H // 2, :]
+    assert (col >= 0).sum() > 40 and len(set(row.tolist()) - {-1, 12}) >= 3      # the centre column / row do see the primitives
+    _check(brt, scene, W, H, max_id_mismatch=8)
+
+
 def test_camera_inside_objects(brt):
     inside_sphere = dict(objects=[dict(type="sphere", center=[0, 0, 0], radius=10.0, material=dict(type="emissive", color=[1, 0.9, 0.8], intensity=0.5)),
                                   dict(type="sphere", center=[0, 0, -2], radius=0.7, material=dict(type="dielectric", ior=1.5))],
