@@ -126,6 +126,14 @@ SIGNATURES = {
     "brt_postprocess_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "brt_eval_texture": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_float)]),
     "brt_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "brt_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]),
+    "brt_device_count": (C.c_int, [C.c_void_p]),
+    "brt_peer_alloc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "brt_peer_connect": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "brt_peer_render": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "brt_peer_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "brt_peer_image_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "brt_peer_free": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

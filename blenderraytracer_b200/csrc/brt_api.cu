@@ -8,54 +8,16 @@
 #include <cstring>
 #include <string>
 #include <vector>
-#include "brt_host.hpp"
-#include "brt_kernels.h"
+#include "brt_ctx.hpp"
 
 using namespace brt;
 
-struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
-        if (e == cudaSuccess) cap = bytes ? bytes : 16;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct brt_ctx {
-    int device = 0;
-    cudaStream_t ownStream = nullptr, stream = nullptr;
-    std::string err;
-    HostScene scene; bool haveScene = false;
-    HostBackground bg;
-    brt_camera cam{}; bool haveCam = false;
-    brt_render_params rp{};
-    // device scene
-    DevBuf dSph, dPln, dBox, dTri, dMeta, dMat, dMatType, dLights, dPerm, dPrim64, dTex, dTexPerm;
-    BvhWorkspace bvhWs;
-    DevScene dev{};
-    bool sceneDirty = true, permDirty = true, bvhDirty = true;
-    int nBounded = 0;
-    brt_scene_info info{};
-    // frame buffers
-    DevBuf dAccum, dRgba, dFloat, dFloat2, dLinear, dCounters, dScratch, dPlanes;
-    // fp64 parity data (lazy)
-    DevBuf dObj64, dTris64; bool obj64Dirty = true;
-    std::atomic<int> cancel{ 0 };
-    brt_stats stats{};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-};
-
-static int fail(brt_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
-static int cuda_fail(brt_ctx* c, cudaError_t e, const char* where) {
+namespace brt {
+int fail(brt_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+int cuda_fail(brt_ctx* c, cudaError_t e, const char* where) {
     return fail(c, BRT_E_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
-#define NEED_GPU() do { if (ctx->device < 0) return fail(ctx, BRT_E_CUDA, "host-only context (device_id = -1): no GPU, and libbrt has no CPU fallback"); } while (0)
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+}
 
 static void default_params(brt_render_params& p) {                 // ray-tracer.js:19-30
     memset(&p, 0, sizeof(p));
@@ -103,12 +65,18 @@ int brt_create(brt_ctx** out, int device_id) {
 void brt_destroy(brt_ctx* ctx) {
     if (!ctx) return;
     if (ctx->device < 0) { delete ctx; return; }
+    for (brt_ctx* f : ctx->followers) { if (f) { cudaSetDevice(f->device); cudaStreamSynchronize(f->stream); } }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->dSph, &ctx->dPln, &ctx->dBox, &ctx->dTri, &ctx->dMeta, &ctx->dMat, &ctx->dMatType, &ctx->dLights, &ctx->dPerm, &ctx->dPrim64, &ctx->dTex, &ctx->dTexPerm,
+    for (brt_ctx* f : ctx->followers) brt_destroy(f);
+    ctx->followers.clear();
+    cudaSetDevice(ctx->device);
+    peer_release(ctx);
+    DevBuf* bufs[] = { &ctx->dArena, &ctx->dPerm, &ctx->dPrim64,
                        &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch, &ctx->dPlanes,
                        &ctx->dObj64, &ctx->dTris64 };
     for (DevBuf* b : bufs) b->release();
+    ctx->hStage.release();
     free_bvh_workspace(&ctx->bvhWs);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -163,7 +131,7 @@ static int scene_load_common(brt_ctx* ctx, const void* data, size_t len, bool bi
                     : load_scene_json((const char*)data, len, fw, fh, sc, bg, cam, hasCam, w, h, err);
     if (rc != BRT_OK) return fail(ctx, rc, err);
     if ((rc = validate_scene(ctx, sc)) != BRT_OK) return rc;
-    ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true;
+    ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true; ctx->sceneVersion++;
     ctx->bg = bg;
     if (hasCam) { ctx->cam = cam; ctx->haveCam = true; }           // ray-tracer.js:315-317
     if (out_has_camera) *out_has_camera = hasCam ? 1 : 0;
@@ -201,118 +169,134 @@ int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {
     }
     int rc = validate_scene(ctx, sc);
     if (rc != BRT_OK) return rc;
-    ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true;
+    ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true; ctx->sceneVersion++;
     return BRT_OK;
 }
 
 static float4 f4(double x, double y, double z, double w) { return make_float4((float)x, (float)y, (float)z, (float)w); }
 
-// Flatten world.objects into per-type SoA float4 arrays + unified meta, upload, build the LBVH.
+// Flatten world.objects into per-type SoA float4 arrays + unified meta.  The arrays are written straight into ONE pinned
+// staging buffer laid out like the device arena, so the whole scene goes up in a single host-to-device copy (the 1.0 M
+// triangle scene: 64 MB, one DMA from page-locked memory).  The float64 primitive copy (prim64, 72 B / primitive) is only
+// needed where primary hits are re-evaluated in float64 and is uploaded on first use (ensure_prim64).
 static int upload_scene(brt_ctx* ctx) {
     NEED_GPU();
     if (!ctx->sceneDirty) return BRT_OK;
     CK(cudaSetDevice(ctx->device));
     auto t0 = std::chrono::steady_clock::now();
-    const HostScene& s = ctx->scene;
-    std::vector<float4> sph, pln, box, tri, mat, lights;
-    std::vector<int4> mSph, mPln, mBox, mTri;
-    std::vector<int> matType;
-    std::vector<double> qSph, qPln, qBox, qTri;                       // float64 copies (9 per primitive) for primary-hit evaluation
-    size_t nTriTotal = 0;
-    for (const brt_object& o : s.objects) nTriTotal += o.type == BRT_OBJ_TRIANGLE ? 1 : o.type == BRT_OBJ_MESH ? (size_t)o.tri_count : 0;
-    if (nTriTotal >= (1u << 28) || s.objects.size() >= (1u << 28)) return fail(ctx, BRT_E_INVALID, "too many primitives (limit 2^28 per type)");
-    // triangles dominate large scenes: sized once, filled by index (no per-triangle push_back / insert)
-    tri.resize(3 * nTriTotal); mTri.resize(nTriTotal); qTri.resize(9 * nTriTotal);
-    size_t triAt = 0;
-    auto push_tri = [&](const double* v0, const double* v1, const double* v2, int obj, int m, int triId) {
-        float4* t = &tri[3 * triAt];
+    const HostScene& s = ctx->hostScene();
+    size_t nSph = 0, nPln = 0, nBox = 0, nTri = 0;
+    for (const brt_object& o : s.objects) {
+        if (o.type == BRT_OBJ_SPHERE) nSph++; else if (o.type == BRT_OBJ_PLANE) nPln++; else if (o.type == BRT_OBJ_BOX) nBox++;
+        else nTri += o.type == BRT_OBJ_TRIANGLE ? 1 : (size_t)o.tri_count;
+    }
+    if (nTri >= (1u << 28) || s.objects.size() >= (1u << 28)) return fail(ctx, BRT_E_INVALID, "too many primitives (limit 2^28 per type)");
+    const size_t nMat = s.materials.size(), nLights = s.lights.size(), nTex = s.textures.size(), nPrim = nSph + nPln + nBox + nTri;
+    // arena layout (256-byte aligned sub-arrays)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+    const size_t oSph = take(nSph * 16), oPln = take(nPln * 32), oBox = take(nBox * 32), oTri = take(nTri * 48), oMeta = take(nPrim * 16),
+                 oMat = take(nMat * 16), oMatType = take(nMat * 4), oLights = take(nLights * 32), oTex = take(nTex * 32), oTexPerm = take(nTex * 512);
+    const size_t arenaBytes = off;
+    CK(ctx->hStage.ensure(arenaBytes));
+    CK(ctx->dArena.ensure(arenaBytes));
+    char* H = (char*)ctx->hStage.p;
+    float4 *sph = (float4*)(H + oSph), *pln = (float4*)(H + oPln), *box = (float4*)(H + oBox), *tri = (float4*)(H + oTri);
+    float4 *mat = (float4*)(H + oMat), *lights = (float4*)(H + oLights), *tex = (float4*)(H + oTex);
+    int4* meta = (int4*)(H + oMeta);
+    int* matType = (int*)(H + oMatType);
+    unsigned char* texPerm = (unsigned char*)(H + oTexPerm);
+    DevScene& d = ctx->dev;
+    d.baseSph = 0; d.basePln = (int)nSph; d.baseBox = (int)(nSph + nPln); d.baseTri = (int)(nSph + nPln + nBox);
+    size_t iS = 0, iP = 0, iB = 0, iT = 0;
+    auto put_tri = [&](const double* v0, const double* v1, const double* v2, int obj, int m, int triId) {
+        float4* t = tri + 3 * iT;
         t[0] = f4(v0[0], v0[1], v0[2], 0);
         // edges are formed in float64 and rounded once (geometry.js:150-151 recomputes them per hit in float64)
         t[1] = f4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], 0);
         t[2] = f4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0);
-        mTri[triAt] = make_int4(obj, m, triId, 0);
-        double* q = &qTri[9 * triAt];
-        memcpy(q, v0, 24); memcpy(q + 3, v1, 24); memcpy(q + 6, v2, 24);
-        triAt++;
-    };
-    auto push9 = [](std::vector<double>& q, const double* a, const double* b, const double* c) {
-        static const double z[3] = { 0, 0, 0 };
-        q.insert(q.end(), a, a + 3); q.insert(q.end(), b ? b : z, (b ? b : z) + 3); q.insert(q.end(), c ? c : z, (c ? c : z) + 3);
+        meta[d.baseTri + iT] = make_int4(obj, m, triId, 0);
+        iT++;
     };
     for (size_t i = 0; i < s.objects.size(); i++) {
         const brt_object& o = s.objects[i];
-        int obj = (int)i;
+        const int obj = (int)i;
         switch (o.type) {
-        case BRT_OBJ_SPHERE: sph.push_back(f4(o.a[0], o.a[1], o.a[2], o.b[0])); mSph.push_back(make_int4(obj, o.material, -1, 0)); push9(qSph, o.a, o.b, nullptr); break;
-        case BRT_OBJ_PLANE: pln.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); pln.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); mPln.push_back(make_int4(obj, o.material, -1, 0)); push9(qPln, o.b, o.a, nullptr); break;
-        case BRT_OBJ_BOX: box.push_back(f4(o.a[0], o.a[1], o.a[2], 0)); box.push_back(f4(o.b[0], o.b[1], o.b[2], 0)); mBox.push_back(make_int4(obj, o.material, -1, 0)); push9(qBox, o.a, o.b, nullptr); break;
-        case BRT_OBJ_TRIANGLE: push_tri(o.a, o.b, o.c, obj, o.material, -1); break;
+        case BRT_OBJ_SPHERE: sph[iS] = f4(o.a[0], o.a[1], o.a[2], o.b[0]); meta[d.baseSph + iS] = make_int4(obj, o.material, -1, 0); iS++; break;
+        case BRT_OBJ_PLANE: pln[2 * iP] = f4(o.b[0], o.b[1], o.b[2], 0); pln[2 * iP + 1] = f4(o.a[0], o.a[1], o.a[2], 0); meta[d.basePln + iP] = make_int4(obj, o.material, -1, 0); iP++; break;
+        case BRT_OBJ_BOX: box[2 * iB] = f4(o.a[0], o.a[1], o.a[2], 0); box[2 * iB + 1] = f4(o.b[0], o.b[1], o.b[2], 0); meta[d.baseBox + iB] = make_int4(obj, o.material, -1, 0); iB++; break;
+        case BRT_OBJ_TRIANGLE: put_tri(o.a, o.b, o.c, obj, o.material, -1); break;
         default:
             for (int64_t t = 0; t < o.tri_count; t++) {
                 const double* p = &s.meshTris[9 * (size_t)(o.first_tri + t)];
-                push_tri(p, p + 3, p + 6, obj, o.material, (int)t);
+                put_tri(p, p + 3, p + 6, obj, o.material, (int)t);
             }
         }
     }
     // material type in the low byte, 1-based texture index above it (TexturedLambertian / TexturedMetal)
-    for (const brt_material& m : s.materials) { mat.push_back(f4(m.color[0], m.color[1], m.color[2], m.param)); matType.push_back(m.type | (m.texture << 8)); }
-    std::vector<float4> tex; std::vector<unsigned char> texPerm;
-    for (const brt_texture& t : s.textures) {
-        tex.push_back(f4(t.odd[0], t.odd[1], t.odd[2], (double)t.kind));
-        tex.push_back(f4(t.even[0], t.even[1], t.even[2], t.scale));
-        for (int k = 0; k < 512; k++) texPerm.push_back(t.perm[k & 255]);      // doubled table (noise.js:16-17)
+    for (size_t i = 0; i < nMat; i++) { const brt_material& m = s.materials[i]; mat[i] = f4(m.color[0], m.color[1], m.color[2], m.param); matType[i] = m.type | (m.texture << 8); }
+    for (size_t i = 0; i < nTex; i++) {
+        const brt_texture& t = s.textures[i];
+        tex[2 * i] = f4(t.odd[0], t.odd[1], t.odd[2], (double)t.kind);
+        tex[2 * i + 1] = f4(t.even[0], t.even[1], t.even[2], t.scale);
+        for (int k = 0; k < 512; k++) texPerm[512 * i + k] = t.perm[k & 255];      // doubled table (noise.js:16-17)
     }
-    for (const brt_light& l : s.lights) {
-        lights.push_back(f4(l.v[0], l.v[1], l.v[2], l.type == BRT_LIGHT_DIRECTIONAL ? 1.0 : 0.0));
-        lights.push_back(f4(l.color[0] * l.intensity, l.color[1] * l.intensity, l.color[2] * l.intensity, 0));
+    for (size_t i = 0; i < nLights; i++) {
+        const brt_light& l = s.lights[i];
+        lights[2 * i] = f4(l.v[0], l.v[1], l.v[2], l.type == BRT_LIGHT_DIRECTIONAL ? 1.0 : 0.0);
+        lights[2 * i + 1] = f4(l.color[0] * l.intensity, l.color[1] * l.intensity, l.color[2] * l.intensity, 0);
     }
-    std::vector<int4> meta;
-    DevScene& d = ctx->dev;
-    d.baseSph = 0; meta.insert(meta.end(), mSph.begin(), mSph.end());
-    d.basePln = (int)meta.size(); meta.insert(meta.end(), mPln.begin(), mPln.end());
-    d.baseBox = (int)meta.size(); meta.insert(meta.end(), mBox.begin(), mBox.end());
-    d.baseTri = (int)meta.size(); meta.insert(meta.end(), mTri.begin(), mTri.end());
-    std::vector<double> prim64;
-    prim64.reserve(qSph.size() + qPln.size() + qBox.size() + qTri.size());
-    prim64.insert(prim64.end(), qSph.begin(), qSph.end()); prim64.insert(prim64.end(), qPln.begin(), qPln.end());
-    prim64.insert(prim64.end(), qBox.begin(), qBox.end()); prim64.insert(prim64.end(), qTri.begin(), qTri.end());
-    d.nSph = (int)mSph.size(); d.nPln = (int)mPln.size(); d.nBox = (int)mBox.size(); d.nTri = (int)mTri.size();
-    d.nLights = (int)s.lights.size();
-    auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
-        cudaError_t e = b.ensure(bytes);
-        if (e != cudaSuccess) return e;
-        if (bytes) e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
-        return e;
-    };
-    CK(up(ctx->dSph, sph.data(), sph.size() * sizeof(float4)));
-    CK(up(ctx->dPln, pln.data(), pln.size() * sizeof(float4)));
-    CK(up(ctx->dBox, box.data(), box.size() * sizeof(float4)));
-    CK(up(ctx->dTri, tri.data(), tri.size() * sizeof(float4)));
-    CK(up(ctx->dMeta, meta.data(), meta.size() * sizeof(int4)));
-    CK(up(ctx->dMat, mat.data(), mat.size() * sizeof(float4)));
-    CK(up(ctx->dMatType, matType.data(), matType.size() * sizeof(int)));
-    CK(up(ctx->dLights, lights.data(), lights.size() * sizeof(float4)));
-    CK(up(ctx->dPrim64, prim64.data(), prim64.size() * sizeof(double)));
-    CK(up(ctx->dTex, tex.data(), tex.size() * sizeof(float4)));
-    CK(up(ctx->dTexPerm, texPerm.data(), texPerm.size()));
-    CK(cudaStreamSynchronize(ctx->stream));
-    d.sph = (const float4*)ctx->dSph.p; d.pln = (const float4*)ctx->dPln.p; d.box = (const float4*)ctx->dBox.p; d.tri = (const float4*)ctx->dTri.p;
-    d.meta = (const int4*)ctx->dMeta.p; d.mat = (const float4*)ctx->dMat.p; d.matType = (const int*)ctx->dMatType.p;
-    d.lights = (const float4*)ctx->dLights.p; d.prim64 = (const double*)ctx->dPrim64.p;
-    d.tex = (const float4*)ctx->dTex.p; d.texPerm = (const unsigned char*)ctx->dTexPerm.p; d.nTex = (int)s.textures.size();
+    d.nSph = (int)nSph; d.nPln = (int)nPln; d.nBox = (int)nBox; d.nTri = (int)nTri;
+    d.nLights = (int)nLights; d.nTex = (int)nTex;
+    if (arenaBytes) CK(cudaMemcpyAsync(ctx->dArena.p, H, arenaBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));                         // the staging buffer is reused by the next upload
+    const char* D = (const char*)ctx->dArena.p;
+    d.sph = (const float4*)(D + oSph); d.pln = (const float4*)(D + oPln); d.box = (const float4*)(D + oBox); d.tri = (const float4*)(D + oTri);
+    d.meta = (const int4*)(D + oMeta); d.mat = (const float4*)(D + oMat); d.matType = (const int*)(D + oMatType);
+    d.lights = (const float4*)(D + oLights); d.tex = (const float4*)(D + oTex); d.texPerm = (const unsigned char*)(D + oTexPerm);
+    d.prim64 = nullptr; ctx->prim64Dirty = true;
     auto t1 = std::chrono::steady_clock::now();
     // the LBVH over the bounded primitives is built on first use (ensure_bvh): tiny scenes render with the linear loop
     d.nodes = nullptr; d.nNodes = 0; d.bvhStackDepth = 0;
     ctx->nBounded = d.nSph + d.nBox + d.nTri;
     ctx->bvhDirty = true;
     brt_scene_info& inf = ctx->info;
-    inf.n_objects = (int)s.objects.size(); inf.n_materials = (int)s.materials.size(); inf.n_lights = (int)s.lights.size();
+    inf.n_objects = (int)s.objects.size(); inf.n_materials = (int)nMat; inf.n_lights = (int)nLights;
     inf.n_spheres = d.nSph; inf.n_planes = d.nPln; inf.n_boxes = d.nBox; inf.n_triangles = d.nTri;
     inf.n_bvh_nodes = 0; inf.bvh_depth = 0; inf.bvh_build_ms = 0;
     inf.upload_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-    inf.upload_bytes = (int64_t)((sph.size() + pln.size() + box.size() + tri.size() + mat.size() + lights.size()) * sizeof(float4) +
-                                 meta.size() * sizeof(int4) + matType.size() * sizeof(int) + prim64.size() * sizeof(double));
+    inf.upload_bytes = (int64_t)arenaBytes;
     ctx->sceneDirty = false;
+    return BRT_OK;
+}
+
+// float64 copy of every primitive (9 doubles, unified index as meta): what refine_primary evaluates.  Uploaded only when a
+// launch needs it (sampler = reference, the fp32 AOV kernel).
+static int ensure_prim64(brt_ctx* ctx) {
+    if (!ctx->prim64Dirty && ctx->dev.prim64) return BRT_OK;
+    const HostScene& s = ctx->hostScene();
+    const DevScene& d = ctx->dev;
+    const size_t nPrim = (size_t)d.nSph + d.nPln + d.nBox + d.nTri;
+    CK(ctx->hStage.ensure(nPrim * 72));
+    CK(ctx->dPrim64.ensure(nPrim * 72));
+    double* q = (double*)ctx->hStage.p;
+    memset(q, 0, nPrim * 72);
+    size_t iS = 0, iP = 0, iB = 0, iT = 0;
+    for (const brt_object& o : s.objects) {
+        switch (o.type) {
+        case BRT_OBJ_SPHERE: { double* r = q + 9 * (d.baseSph + iS++); memcpy(r, o.a, 24); memcpy(r + 3, o.b, 24); break; }
+        case BRT_OBJ_PLANE: { double* r = q + 9 * (d.basePln + iP++); memcpy(r, o.b, 24); memcpy(r + 3, o.a, 24); break; }
+        case BRT_OBJ_BOX: { double* r = q + 9 * (d.baseBox + iB++); memcpy(r, o.a, 24); memcpy(r + 3, o.b, 24); break; }
+        case BRT_OBJ_TRIANGLE: { double* r = q + 9 * (d.baseTri + iT++); memcpy(r, o.a, 24); memcpy(r + 3, o.b, 24); memcpy(r + 6, o.c, 24); break; }
+        default:
+            if (o.tri_count > 0) memcpy(q + 9 * (d.baseTri + iT), &s.meshTris[9 * (size_t)o.first_tri], 72 * (size_t)o.tri_count);
+            iT += (size_t)o.tri_count;
+        }
+    }
+    if (nPrim) CK(cudaMemcpyAsync(ctx->dPrim64.p, q, nPrim * 72, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dev.prim64 = (const double*)ctx->dPrim64.p;
+    ctx->prim64Dirty = false;
     return BRT_OK;
 }
 
@@ -350,7 +334,7 @@ int brt_scene_info_get(brt_ctx* ctx, brt_scene_info* out) {
     if (!ctx->haveScene) return fail(ctx, BRT_E_NOSCENE, "no scene loaded");
     if (ctx->device < 0) {
         memset(out, 0, sizeof(*out));
-        const HostScene& s = ctx->scene;
+        const HostScene& s = ctx->hostScene();
         out->n_objects = (int)s.objects.size(); out->n_materials = (int)s.materials.size(); out->n_lights = (int)s.lights.size();
         for (const brt_object& o : s.objects) {
             if (o.type == BRT_OBJ_SPHERE) out->n_spheres++; else if (o.type == BRT_OBJ_PLANE) out->n_planes++;
@@ -425,11 +409,26 @@ int brt_get_render_params(brt_ctx* ctx, brt_render_params* out) {
     return BRT_OK;
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------- render
 static bool use_bvh(const brt_ctx* ctx) { return wants_bvh(ctx) && !ctx->bvhDirty && ctx->dev.nNodes > 0; }
-static int effective_spp(const brt_render_params& rp) { return rp.aa_mode == BRT_AA_NONE ? 1 : rp.spp; }    // ray-tracer.js:201
+namespace brt {
+int effective_spp(const brt_render_params& rp) { return rp.aa_mode == BRT_AA_NONE ? 1 : rp.spp; }    // ray-tracer.js:201
+int spp_batch(const brt_ctx* ctx, int spp, bool haveCallback) {
+    int batch = ctx->rp.spp_batch > 0 ? ctx->rp.spp_batch : (haveCallback ? (spp + 15) / 16 : spp);
+    if (ctx->rp.spp_batch <= 0) {
+        // keep one launch to a few seconds at most so brt_cancel is honoured promptly (it is polled between launches):
+        // about 4e9 path samples per launch
+        const long long px = (long long)ctx->rp.width * ctx->rp.height;
+        long long cap = 4000000000LL / (px ? px : 1);
+        if (cap < 1) cap = 1;
+        if (batch > cap) batch = (int)cap;
+    }
+    return batch < 1 ? 1 : batch;
+}
 
-static int prepare(brt_ctx* ctx, PTParams& p) {
+int prepare(brt_ctx* ctx, PTParams& p) {
     NEED_GPU();
     if (!ctx->haveScene) return fail(ctx, BRT_E_NOSCENE, "no scene loaded");
     if (!ctx->haveCam) return fail(ctx, BRT_E_NOSCENE, "no camera set");
@@ -439,6 +438,7 @@ static int prepare(brt_ctx* ctx, PTParams& p) {
     if (wants_bvh(ctx) && (rc = ensure_bvh(ctx)) != BRT_OK) return rc;
     if ((rc = upload_perm(ctx)) != BRT_OK) return rc;
     const brt_render_params& rp = ctx->rp;
+    if (rp.sampler == BRT_SAMPLER_REFERENCE && (rc = ensure_prim64(ctx)) != BRT_OK) return rc;   // float64 primary-hit evaluation
     memset(&p, 0, sizeof(p));
     ctx->dev.bgKind = ctx->bg.kind; ctx->dev.bgR = (float)ctx->bg.color[0]; ctx->dev.bgG = (float)ctx->bg.color[1];
     ctx->dev.bgB = (float)ctx->bg.color[2]; ctx->dev.skyIntensity = (float)ctx->bg.intensity;
@@ -467,7 +467,7 @@ static int prepare(brt_ctx* ctx, PTParams& p) {
 }
 
 static int z_split(const brt_ctx* ctx, int samplesInLaunch) {
-    // keep >= ~4 resident waves of threads on 148 SMs when the image is small (then atomics merge the chunks)
+    // keep >= ~4 resident waves of threads on 148 SMs when the image is small (the chunks' planes are folded in fixed order)
     const long long want = 148LL * 2048 * 2;
     long long px = (long long)ctx->rp.width * ctx->rp.height;
     if (px >= want || samplesInLaunch < 2) return 1;
@@ -477,7 +477,14 @@ static int z_split(const brt_ctx* ctx, int samplesInLaunch) {
     return (int)z;
 }
 
-static int launch_samples(brt_ctx* ctx, PTParams& p, float* dAccum, int sBegin, int sCount) {
+int reserve_launch_buffers(brt_ctx* ctx, int maxSamplesPerLaunch) {
+    const int z = z_split(ctx, maxSamplesPerLaunch);
+    if (z > 1) CK(ctx->dPlanes.ensure((size_t)ctx->rp.width * ctx->rp.height * 16 * (size_t)z));
+    if (ctx->rp.count_tests) CK(ctx->dCounters.ensure(N_COUNTERS * sizeof(unsigned long long)));
+    return BRT_OK;
+}
+
+int launch_samples(brt_ctx* ctx, PTParams& p, float* dAccum, int sBegin, int sCount) {
     p.accum = (float4*)dAccum; p.sBegin = sBegin; p.sCount = sCount;
     const bool count = ctx->rp.count_tests != 0;
     if (count) {
@@ -503,7 +510,7 @@ static int launch_samples(brt_ctx* ctx, PTParams& p, float* dAccum, int sBegin, 
     return BRT_OK;
 }
 
-static PostParams post_params(const brt_ctx* ctx) {
+PostParams post_params(const brt_ctx* ctx) {
     PostParams pp{};
     pp.W = ctx->rp.width; pp.H = ctx->rp.height; pp.tonemap = ctx->rp.tonemap; pp.exposure = ctx->rp.exposure;
     pp.invGamma = 1.0 / ctx->rp.gamma;                              // post-processor.js:36
@@ -511,6 +518,10 @@ static PostParams post_params(const brt_ctx* ctx) {
     pp.w1 = std::exp(-1.0 / (2 * s * s)); pp.w2 = std::exp(-2.0 / (2 * s * s));   // post-processor.js:59
     return pp;
 }
+
+}  // namespace brt
+
+extern "C" {
 
 int brt_render_accumulate(brt_ctx* ctx, float* d_accum, int sample_begin, int sample_count) {
     if (!ctx) return BRT_E_INVALID;
@@ -628,6 +639,7 @@ int brt_copy_to_host(brt_ctx* ctx, void* host_dst, const void* d_src, size_t byt
 
 int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_mean, brt_progress_cb cb, void* user) {
     if (!ctx || !rgba8) return BRT_E_INVALID;
+    if (!ctx->followers.empty()) return render_multi(ctx, rgba8, float_data, linear_mean, cb, user);   // brt_create_multi: n GPUs behind the same call
     auto w0 = std::chrono::steady_clock::now();
     ctx->cancel.store(0);
     PTParams p;
@@ -641,15 +653,7 @@ int brt_render(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_me
     if (ctx->rp.count_tests) { CK(ctx->dCounters.ensure(N_COUNTERS * 8)); CK(cudaMemsetAsync(ctx->dCounters.p, 0, N_COUNTERS * 8, ctx->stream)); }
     ctx->stats = brt_stats{};
     const int spp = effective_spp(ctx->rp);
-    int batch = ctx->rp.spp_batch > 0 ? ctx->rp.spp_batch : (cb ? (spp + 15) / 16 : spp);
-    if (ctx->rp.spp_batch <= 0) {
-        // keep one launch to a few seconds at most so brt_cancel is honoured promptly (it is polled between launches):
-        // about 4e9 path samples per launch
-        long long cap = 4000000000LL / (long long)(px ? px : 1);
-        if (cap < 1) cap = 1;
-        if (batch > cap) batch = (int)cap;
-    }
-    if (batch < 1) batch = 1;
+    const int batch = spp_batch(ctx, spp, cb != nullptr);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int s = 0; s < spp; s += batch) {
         int n = spp - s < batch ? spp - s : batch;
@@ -716,6 +720,8 @@ int brt_primary_aov_f32(brt_ctx* ctx, int32_t* obj_id, int32_t* tri_id, float* t
     PTParams p;
     int rc = prepare(ctx, p);
     if (rc != BRT_OK) return rc;
+    if ((rc = ensure_prim64(ctx)) != BRT_OK) return rc;
+    p.sc = ctx->dev;
     size_t px = (size_t)p.W * p.H;
     CK(ctx->dScratch.ensure(px * (4 + 4 + 4 + 12 + 1) + 64));
     char* base = (char*)ctx->dScratch.p;

@@ -58,6 +58,25 @@ cudaError_t launch_reduce_resolve(const PostParams& pp, const float4* const* pee
                                   int rowBegin, int rowEnd, cudaStream_t st);
 cudaError_t launch_denoise(const PostParams& pp, const float4* floatData, uchar4* rgba, float4* outFloat, cudaStream_t st);
 
+// The synchronised form of the fused exchange (brt_multi.cu): every rank owns three flag words in its peer-mapped block —
+//   FLAG_READY: the epoch whose sums this rank has finished tracing;  FLAG_DONE: the epoch whose row stripe this rank has
+//   resolved into the root's image;  FLAG_BLOCKS: completion counter of the stripe kernel;  FLAG_ERR: a wait timed out.
+constexpr int MAX_PEERS = 16;
+enum PeerFlag : int { FLAG_READY = 0, FLAG_DONE = 1, FLAG_BLOCKS = 2, FLAG_ERR = 3, FLAG_WORDS = 64 };
+struct PeerSync {
+    const float4* accum[MAX_PEERS];   // every rank's sums of this epoch (peer-mapped), rank order
+    unsigned* flags[MAX_PEERS];       // every rank's flag words (peer-mapped)
+    int nPeers, self;
+    unsigned epoch;
+};
+// k_peer_reduce_resolve: publishes READY(self) = epoch, waits until READY(r) >= epoch for every rank (acquire at system scope),
+// sums rows [rowBegin, rowEnd) of all ranks' buffers in rank order, resolves, stores RGBA8 (+ floatData / linear) into the
+// ROOT's image, and the last block to finish publishes DONE(self) = epoch.
+cudaError_t launch_peer_reduce_resolve(const PostParams& pp, const PeerSync& ps, uchar4* rgbaRoot, float4* floatRoot, float4* linearRoot,
+                                       int rowBegin, int rowEnd, cudaStream_t st);
+// k_peer_wait: one block that spins until flag `which` of every rank reached ps.epoch (the root runs it with FLAG_DONE before it reads its image)
+cudaError_t launch_peer_wait(const PeerSync& ps, int which, cudaStream_t st);
+
 // aov64.cu — float64, FMA-free, brute-force primary visibility with the reference's exact operation order
 struct Obj64 {                   // one per world.objects entry, in order
     int type, material;

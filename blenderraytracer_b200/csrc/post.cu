@@ -62,6 +62,56 @@ __global__ void __launch_bounds__(256) k_reduce_resolve(PostParams pp, PeerPtrs 
     resolve_pixel(pp, s, k, rgba, floatData, nullptr);
 }
 
+// ---- synchronised cross-GPU exchange: device-side epoch flags in peer-mapped memory (no host or NCCL barrier) -------------
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;   // a peer that never arrives must not hang the GPU
+
+// thread r < nPeers waits for rank r; epochs only grow, so >= (as a signed difference: wrap-safe)
+__device__ __forceinline__ void wait_all(const PeerSync& ps, int which) {
+    if ((int)threadIdx.x < ps.nPeers) {
+        const unsigned* f = ps.flags[threadIdx.x] + which;
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(f) - ps.epoch) < 0) {
+            __nanosleep(200);
+            if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { atomicExch(ps.flags[ps.self] + FLAG_ERR, 1u); break; }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_peer_reduce_resolve(PostParams pp, PeerSync ps, uchar4* rgba, float4* floatData, float4* linear,
+                                                             size_t begin, size_t end) {
+    unsigned* mine = ps.flags[ps.self];
+    // the stream ordered this kernel after this rank's path-tracing launch: its sums are complete and, after the fence, visible to peers
+    if (blockIdx.x == 0 && threadIdx.x == 0) { __threadfence_system(); st_release_sys(mine + FLAG_READY, ps.epoch); }
+    wait_all(ps, FLAG_READY);
+    size_t k = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < end) {
+        float4 s = __ldcg(ps.accum[0] + k);
+        for (int r = 1; r < ps.nPeers; r++) {                         // fixed rank order: the sum is deterministic
+            float4 v = __ldcg(ps.accum[r] + k);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        resolve_pixel(pp, s, k, rgba, floatData, linear);
+    }
+    __threadfence_system();                                           // this thread's stores into the root's image are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {                                           // ... before the last block publishes DONE
+        if (atomicAdd(mine + FLAG_BLOCKS, 1u) == gridDim.x - 1) {
+            mine[FLAG_BLOCKS] = 0u;
+            __threadfence_system();
+            st_release_sys(mine + FLAG_DONE, ps.epoch);
+        }
+    }
+}
+__global__ void __launch_bounds__(32) k_peer_wait(PeerSync ps, int which) { wait_all(ps, which); }
+
 // post-processor.js:45-77 — clamp-to-edge 3x3, weights exp(-(kx²+ky²)/(2σ²)), accumulation order ky outer / kx inner.
 __global__ void __launch_bounds__(256) k_denoise(PostParams pp, const float4* __restrict__ in, uchar4* rgba, float4* outFloat) {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -102,6 +152,19 @@ cudaError_t launch_reduce_resolve(const PostParams& pp, const float4* const* pee
     if (end <= begin) return cudaSuccess;
     unsigned blocks = (unsigned)((end - begin + 255) / 256);
     k_reduce_resolve<<<blocks, 256, 0, st>>>(pp, pr, nPeers, rgba, floatData, begin, end);
+    return cudaGetLastError();
+}
+cudaError_t launch_peer_reduce_resolve(const PostParams& pp, const PeerSync& ps, uchar4* rgbaRoot, float4* floatRoot, float4* linearRoot,
+                                       int rowBegin, int rowEnd, cudaStream_t st) {
+    if (ps.nPeers < 1 || ps.nPeers > MAX_PEERS) return cudaErrorInvalidValue;
+    size_t begin = (size_t)rowBegin * pp.W, end = (size_t)rowEnd * pp.W;
+    // an empty stripe still takes part in the flag protocol (READY / DONE), with one block
+    unsigned blocks = end > begin ? (unsigned)((end - begin + 255) / 256) : 1u;
+    k_peer_reduce_resolve<<<blocks, 256, 0, st>>>(pp, ps, rgbaRoot, floatRoot, linearRoot, begin, end);
+    return cudaGetLastError();
+}
+cudaError_t launch_peer_wait(const PeerSync& ps, int which, cudaStream_t st) {
+    k_peer_wait<<<1, 32, 0, st>>>(ps, which);
     return cudaGetLastError();
 }
 cudaError_t launch_denoise(const PostParams& pp, const float4* floatData, uchar4* rgba, float4* outFloat, cudaStream_t st) {

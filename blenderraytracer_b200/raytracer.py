@@ -50,10 +50,16 @@ def make_perm(seed: int) -> np.ndarray:
 
 
 class RayTracer:
-    def __init__(self, width=600, height=400, device=0, seed=1, perm_seed=0, stream=None):
+    def __init__(self, width=600, height=400, device=0, seed=1, perm_seed=0, stream=None, devices=None):
+        """`devices=[0, 1, ...]`: one context spanning several GPUs of this process (brt_create_multi) — render() is still
+        one call, every batch's samples are split over the devices and exchanged by the fused peer kernel."""
         self._L = L.load()
         h = C.c_void_p()
-        rc = self._L.brt_create(C.byref(h), int(device))
+        if devices is not None and len(devices) > 0:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._L.brt_create_multi(C.byref(h), ids, len(devices))
+        else:
+            rc = self._L.brt_create(C.byref(h), int(device))
         if rc != L.BRT_OK:
             raise L.BrtError(rc, "brt_create failed — libbrt needs a CUDA device (sm_100a); there is no CPU fallback "
                                  "(device=-1 gives a host-only context for scene/camera logic, which cannot render)")
@@ -391,6 +397,14 @@ class RayTracer:
         self.floatData, self.linearMean = fdat, lin
         return rgba
 
+    def renderInto(self, rgba_ptr, float_ptr=None, linear_ptr=None, onProgress=None):
+        """brt_render straight into caller-owned HOST buffers (addresses): the call the N-API addon makes with the backing
+        store of imageData.data (ray-tracer.js:166-281).  No numpy allocation, no extra copy."""
+        self._push_params()
+        cb = L.PROGRESS_CB(lambda f, _u: onProgress(f)) if onProgress else L.PROGRESS_CB()
+        vp = lambda p: C.c_void_p(int(p)) if p else None
+        L.check(self._ctx, self._L.brt_render(self._ctx, vp(rgba_ptr), vp(float_ptr), vp(linear_ptr), cb, None))
+
     def cancel(self):                                                  # window.renderCancelled = true (ui-controller.js:134-137)
         self._L.brt_cancel(self._ctx)
 
@@ -539,3 +553,32 @@ class RayTracer:
 
     def synchronize(self):
         L.check(self._ctx, self._L.brt_stream_synchronize(self._ctx))
+
+    # peer group: one process per GPU, exchange fused into the resolve kernel (include/brt.h, brt_peer_*)
+    def deviceCount(self) -> int:
+        return int(self._L.brt_device_count(self._ctx))
+
+    def peerAlloc(self, rank, world) -> bytes:
+        self._push_params()                                            # the block is sized from width x height
+        h = C.create_string_buffer(64)
+        L.check(self._ctx, self._L.brt_peer_alloc(self._ctx, int(rank), int(world), h))
+        return h.raw
+
+    def peerConnect(self, handles):
+        blob = b"".join(bytes(h) for h in handles)
+        L.check(self._ctx, self._L.brt_peer_connect(self._ctx, C.create_string_buffer(blob, len(blob))))
+
+    def peerRender(self, sample_begin, sample_count, want_float=False, want_linear=False):
+        L.check(self._ctx, self._L.brt_peer_render(self._ctx, int(sample_begin), int(sample_count), int(want_float), int(want_linear)))
+
+    def peerFetch(self, rgba_ptr=None, float_ptr=None, linear_ptr=None):
+        vp = lambda p: C.c_void_p(int(p)) if p else None
+        L.check(self._ctx, self._L.brt_peer_fetch(self._ctx, vp(rgba_ptr), vp(float_ptr), vp(linear_ptr)))
+
+    def peerImagePtr(self) -> int:
+        p = C.c_void_p()
+        L.check(self._ctx, self._L.brt_peer_image_ptr(self._ctx, C.byref(p)))
+        return p.value
+
+    def peerFree(self):
+        L.check(self._ctx, self._L.brt_peer_free(self._ctx))

@@ -12,9 +12,9 @@
  *   - C linkage, plain pointers and sizes only; no exceptions cross the boundary.
  *   - Every call returns BRT_OK (0) or a negative BRT_E_* code; brt_last_error(ctx) returns a ctx-owned
  *     NUL-terminated message that stays valid until the next call on that ctx.
- *   - A ctx is bound to ONE CUDA device (one process per GPU; multi-GPU = one ctx per rank, see
- *     brt_render_accumulate / brt_resolve_device / brt_peer_*).  A ctx is not re-entrant: one call at a
- *     time, except brt_cancel which may be called from any thread.
+ *   - brt_create binds a ctx to ONE CUDA device; brt_create_multi spans several devices of one process behind the same
+ *     calls; with one process per GPU every rank owns a ctx and joins a peer group (brt_peer_*).  A ctx is not
+ *     re-entrant: one call at a time, except brt_cancel which may be called from any thread.
  *   - Host descriptors are double precision (JavaScript Numbers are doubles); the device path computes in
  *     fp32 except where stated.
  *   - Images are row-major with row 0 = TOP (pixelIndex = ((H-1-j)*W + i)*4, ray-tracer.js:215).
@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BRT_ABI_VERSION 1
+#define BRT_ABI_VERSION 2
 
 typedef struct brt_ctx brt_ctx;
 
@@ -252,7 +252,34 @@ int brt_resolve_device(brt_ctx* ctx, const float* d_accum, uint8_t* d_rgba8, flo
 int brt_reduce_resolve_peers(brt_ctx* ctx, const float* const* d_peer_accum, int n_peers, int row_begin, int row_end,
                              uint8_t* d_rgba8_root, float* d_float_data_root);
 int brt_stream_synchronize(brt_ctx* ctx);
-/* Buffers for the cross-process (one process per GPU) form of the fused reduce: cudaMalloc'd by the library so that a
+
+/* ---- multi-GPU: the samples-per-pixel split with the exchange fused into its consumer ------------------------
+ * (a) ONE process, n GPUs — what a Node host binds: a context that spans the listed devices.  Every other call is unchanged:
+ *     brt_render(ctx, host_rgba8, ...) splits each batch's samples over the devices, every device traces its share, one fused
+ *     kernel per device pulls its row stripe of all devices' fp32 sums over NVLink (peer access), sums in device order,
+ *     tone-maps and stores RGBA8 into device 0's image, which is copied into the caller's buffer.  The reference's caller
+ *     still makes ONE call (js/ui-controller.js:189 `await raytracer.render(cb)`).  Scene / camera / parameter setters on
+ *     the returned context apply to all devices.  n = 1 is the same as brt_create. */
+int brt_create_multi(brt_ctx** out, const int* device_ids, int n_devices);
+int brt_device_count(const brt_ctx* ctx);
+/* (b) ONE process PER GPU (torchrun / MPI): rank r of `world` allocates its exchange block (sized from the current render
+ *     params; double-buffered fp32 sums, RGBA8 / floatData / linear images, three epoch flag words) and gets a 64-byte CUDA
+ *     IPC handle for it; the caller gathers the handles of all ranks (world x 64 bytes, rank order) and every rank connects.
+ *     brt_peer_render then runs one exchange epoch asynchronously on the ctx stream: zero, trace this rank's samples
+ *     [sample_begin, sample_begin + sample_count), publish "ready", wait for every peer's flag (acquire loads on peer-mapped
+ *     memory: no host barrier, no NCCL), reduce this rank's row stripe in rank order, resolve, store into RANK 0's image.
+ *     Every rank must call it once per epoch with its own sample range.  brt_peer_fetch on rank 0 waits until all stripes
+ *     have arrived and copies the image(s) into HOST buffers (any may be NULL); on other ranks it only synchronises.
+ *     A peer that never arrives makes the wait time out after 20 s (BRT_E_STATE), it cannot hang the GPU. */
+int brt_peer_alloc(brt_ctx* ctx, int rank, int world, uint8_t handle[64]);
+int brt_peer_connect(brt_ctx* ctx, const uint8_t* handles /* world x 64 bytes */);
+int brt_peer_render(brt_ctx* ctx, int sample_begin, int sample_count, int want_float_data, int want_linear_mean);
+int brt_peer_fetch(brt_ctx* ctx, uint8_t* rgba8, float* float_data, float* linear_mean);
+int brt_peer_image_ptr(brt_ctx* ctx, void** d_rgba8);      /* this rank's RGBA8 image region (the group's image on rank 0), DEVICE pointer */
+int brt_peer_free(brt_ctx* ctx);
+
+/* ---- unsynchronised building blocks of the same exchange (the caller orders the ranks itself, e.g. with NCCL) --------------
+ * Buffers for the cross-process (one process per GPU) form of the fused reduce: cudaMalloc'd by the library so that a
  * CUDA IPC handle (64 opaque bytes, sent to the peers by the caller, e.g. torch.distributed.all_gather_object) names
  * them.  brt_shared_open maps a peer's buffer into this process (NVLink peer access); close before the owner frees. */
 int brt_shared_alloc(brt_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]);

@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import pytest
 
-from blenderraytracer_b200.distributed import reduce_sums, row_stripe, sample_range
+from blenderraytracer_b200.distributed import equal_stripe, reduce_scatter_sums, reduce_sums, row_stripe, sample_range
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -34,6 +34,17 @@ def test_row_stripes_cover_the_image():
             rows = [row_stripe(h, r, world) for r in range(world)]
             assert rows[0][0] == 0 and rows[-1][1] == h
             assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+def test_equal_stripes_cover_the_padded_image():
+    for h in (1, 7, 1080, 2160, 401):
+        for world in (1, 2, 3, 4, 8):
+            parts = [equal_stripe(h, r, world) for r in range(world)]
+            s = parts[0][0]
+            assert s * world >= h and all(p[0] == s for p in parts)
+            assert parts[0][1] == 0 and max(p[2] for p in parts) == h
+            assert all(a[2] == b[1] or b[1] == h for a, b in zip(parts, parts[1:]))     # contiguous until the image ends
+            assert sum(p[2] - p[1] for p in parts) == h
 
 
 def _free_port():
@@ -62,8 +73,17 @@ def _worker(rank, world, port, spp, W, H, q):
             o.render()
             accum[..., :3] = torch.from_numpy(o.linear[..., :3] * count)     # the device kernel accumulates SUMS, alpha = count
             accum[..., 3] = count
+        # the NCCL fallback's exchange: reduce_scatter of the padded sums -> every rank owns the sum of its equal row stripe
+        S, r0, r1 = equal_stripe(H, rank, world)
+        padded = torch.zeros((S * world, W, 4), dtype=torch.float64)
+        padded[:H] = accum
+        stripe = torch.zeros((S, W, 4), dtype=torch.float64)
+        reduce_scatter_sums(padded, stripe)
+        stripes = [torch.zeros_like(stripe) for _ in range(world)]
+        dist.all_gather(stripes, stripe)
         reduce_sums(accum, dst=0)
         if rank == 0:
+            assert torch.equal(torch.cat(stripes)[:H], accum), "reduce_scatter + all_gather of stripes differs from reduce-to-root"
             q.put(accum.numpy())
     finally:
         dist.destroy_process_group()
