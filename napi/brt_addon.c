@@ -7,7 +7,8 @@
  * the reference's `await new Promise(r => setTimeout(r, 0))` yields (:241,:261) — and reports progress through a
  * thread-safe function; cancel() maps window.renderCancelled (:190,:256,:264) onto brt_cancel.
  *
- * Build (needs Node headers; this repo's image has none, so build() only syntax-checks against node_api_min.h):
+ * Build (with Node headers; this repo's image has none, so __graft_entry__.build() compiles against node_api_min.h — the same
+ * C ABI — and tests/test_napi_mock.py loads the result into a mock N-API host and runs it end to end):
  *   cc -shared -fPIC -I../include -I$(node -p "process.execPath+'/../../include/node'") brt_addon.c \
  *      -L../blenderraytracer_b200 -lbrt -Wl,-rpath,'$ORIGIN/../blenderraytracer_b200' -o brt_addon.node
  */
@@ -58,13 +59,24 @@ static double get_f64(napi_env env, napi_value obj, const char* key, double dflt
     return r;
 }
 
-/* create(deviceId) -> external */
+/* create(deviceId | [deviceId, ...]) -> external.  An array makes ONE context that spans several GPUs (brt_create_multi):
+ * render() stays one call, the samples of every batch are split over the devices and exchanged by the fused peer kernel. */
 static napi_value js_create(napi_env env, napi_callback_info info) {
     ARGS(1);
-    int32_t dev = 0; if (argc >= 1) napi_get_value_int32(env, argv[0], &dev);
     brt_ctx* ctx = NULL;
-    int rc = brt_create(&ctx, dev);
-    if (rc != BRT_OK) { napi_throw_error(env, "BRT_E_CUDA", "brt_create failed: libbrt needs a CUDA device (no CPU fallback)"); return NULL; }
+    int rc;
+    bool is_arr = false;
+    if (argc >= 1 && napi_is_array(env, argv[0], &is_arr) == napi_ok && is_arr) {
+        uint32_t n = 0; napi_get_array_length(env, argv[0], &n);
+        int ids[16];
+        if (n < 1 || n > 16) { napi_throw_error(env, "BRT_E_INVALID", "devices: 1..16 CUDA device ids"); return NULL; }
+        for (uint32_t i = 0; i < n; i++) { napi_value e; int32_t d = 0; napi_get_element(env, argv[0], i, &e); napi_get_value_int32(env, e, &d); ids[i] = d; }
+        rc = brt_create_multi(&ctx, ids, (int)n);
+    } else {
+        int32_t dev = 0; if (argc >= 1) napi_get_value_int32(env, argv[0], &dev);
+        rc = brt_create(&ctx, dev);
+    }
+    if (rc != BRT_OK) { napi_throw_error(env, rc == BRT_E_INVALID ? "BRT_E_INVALID" : "BRT_E_CUDA", "brt_create failed: libbrt needs CUDA device(s) it can use (no CPU fallback)"); return NULL; }
     napi_value ext; napi_create_external(env, ctx, finalize_ctx, NULL, &ext);
     return ext;
 }
@@ -89,7 +101,7 @@ static napi_value js_load_scene_json(napi_env env, napi_callback_info info) {
     return out;
 }
 
-/* setSceneFlat(ctx, objects Float64Array[13 n], materials Float64Array[5 m], meshTris Float64Array[9 t], lights Float64Array[8 l])
+/* setSceneFlat(ctx, objects Float64Array[13 n], materials Float64Array[6 m], meshTris Float64Array[9 t], lights Float64Array[8 l])
  * objects: type, material, a.xyz, b.xyz, c.xyz, firstTri, triCount — one row per world.objects entry, in order (world.js:24-30)
  * materials: type, r, g, b, param, texture(1-based, 0 = none) — 6 per material
  * optional: textures Float64Array[8 k] (kind, odd.rgb, even.rgb, scale) + texturePerms Uint8Array[256 k]   (js/textures.js) */
@@ -190,7 +202,7 @@ static napi_value js_set_render_params(napi_env env, napi_callback_info info) {
 /* render(ctx, data Uint8ClampedArray[W*H*4], onProgress?) -> Promise<void>   (RayTracer.render, ray-tracer.js:166-281) */
 typedef struct {
     brt_ctx* ctx; uint8_t* rgba; int rc; char err[256];
-    napi_deferred deferred; napi_async_work work; napi_ref data_ref; napi_threadsafe_function tsfn;
+    napi_deferred deferred; napi_async_work work; napi_ref data_ref, ctx_ref; napi_threadsafe_function tsfn;
 } render_job;
 static void progress_from_worker(double fraction, void* user) {
     render_job* j = (render_job*)user;
@@ -227,6 +239,7 @@ static void render_complete(napi_env env, napi_status status, void* data) {
     }
     if (j->tsfn) napi_release_threadsafe_function(j->tsfn, napi_tsfn_release);
     napi_delete_reference(env, j->data_ref);
+    napi_delete_reference(env, j->ctx_ref);
     napi_delete_async_work(env, j->work);
     free(j);
 }
@@ -244,6 +257,7 @@ static napi_value js_render(napi_env env, napi_callback_info info) {
     napi_value promise, name;
     napi_create_promise(env, &j->deferred, &promise);
     napi_create_reference(env, argv[1], 1, &j->data_ref);          /* keep the pixel buffer alive while the worker writes it */
+    napi_create_reference(env, argv[0], 1, &j->ctx_ref);           /* and the ctx: dropping the handle mid-render must not run finalize_ctx -> brt_destroy */
     napi_create_string_utf8(env, "brt_render", NAPI_AUTO_LENGTH, &name);
     napi_valuetype t = napi_undefined;
     if (argc >= 3) napi_typeof(env, argv[2], &t);
@@ -272,6 +286,7 @@ static napi_value js_stats(napi_env env, napi_callback_info info) {
     napi_create_double(env, s.post_ms, &v); napi_set_named_property(env, out, "postMs", v);
     napi_create_double(env, s.total_ms, &v); napi_set_named_property(env, out, "totalMs", v);
     napi_create_double(env, (double)s.launches, &v); napi_set_named_property(env, out, "launches", v);
+    napi_create_int32(env, brt_device_count(ctx), &v); napi_set_named_property(env, out, "devices", v);
     return out;
 }
 

@@ -1,7 +1,7 @@
 /* mock_node_host.c — a stand-in for Node.js that is just enough of an N-API host to LOAD and DRIVE brt_addon.node.
  *
  * TEST INFRASTRUCTURE.  This image has no Node.js, so the addon could otherwise only be compiled, never run.  This
- * program implements the 30-odd napi_* functions the addon imports over a tiny tagged-value heap, dlopen()s the addon
+ * program implements the 36 napi_* functions the addon imports over a tiny tagged-value heap, dlopen()s the addon
  * (the napi_* symbols resolve against this executable, as they do against `node`), calls napi_register_module_v1 and
  * then drives the exported functions the way napi/raytracer_gpu.mjs does:
  *     create -> loadSceneJSON -> setRenderParams -> render(ctx, Uint8ClampedArray, onProgress) -> Promise
@@ -28,6 +28,7 @@ typedef struct Val {
     napi_callback fn; void* fn_data;                               /* function */
     int is_typed; napi_typedarray_type ta_type; void* ta_data; size_t ta_len;   /* typed array (type == napi_object) */
     int is_error; int is_promise; int settled; struct Val* result;              /* promise: settled 1 = resolved, 2 = rejected */
+    int is_array; struct Val** elems; uint32_t n_elems;                         /* Array (type == napi_object) */
     struct Val* (*native)(struct Val** argv, size_t argc);         /* host-side JS function (onProgress) */
 } Val;
 struct napi_callback_info__ { size_t argc; Val** argv; void* data; };
@@ -51,6 +52,9 @@ napi_status napi_create_string_utf8(napi_env e, const char* s, size_t n, napi_va
     x->str = (char*)malloc(n + 1); memcpy(x->str, s, n); x->str[n] = 0; *r = NV(x); return napi_ok;
 }
 napi_status napi_typeof(napi_env e, napi_value v, napi_valuetype* r) { (void)e; *r = V(v)->type; return napi_ok; }
+napi_status napi_is_array(napi_env e, napi_value v, bool* r) { (void)e; *r = V(v)->is_array != 0; return napi_ok; }
+napi_status napi_get_array_length(napi_env e, napi_value v, uint32_t* r) { (void)e; if (!V(v)->is_array) return napi_array_expected; *r = V(v)->n_elems; return napi_ok; }
+napi_status napi_get_element(napi_env e, napi_value v, uint32_t i, napi_value* r) { (void)e; *r = NV(V(v)->is_array && i < V(v)->n_elems ? V(v)->elems[i] : &UNDEF); return napi_ok; }
 napi_status napi_get_value_int32(napi_env e, napi_value v, int32_t* r) { (void)e; if (V(v)->type != napi_number) return napi_number_expected; *r = (int32_t)V(v)->num; return napi_ok; }
 napi_status napi_get_value_double(napi_env e, napi_value v, double* r) { (void)e; if (V(v)->type != napi_number) return napi_number_expected; *r = V(v)->num; return napi_ok; }
 napi_status napi_get_value_bool(napi_env e, napi_value v, bool* r) { (void)e; if (V(v)->type != napi_boolean) return napi_boolean_expected; *r = V(v)->b; return napi_ok; }
@@ -146,7 +150,15 @@ int main(int argc, char** argv) {
     char* text = (char*)malloc(n + 1); if (fread(text, 1, n, f) != (size_t)n) return 2; text[n] = 0; fclose(f);
     int W = atoi(argv[3]), H = atoi(argv[4]), spp = atoi(argv[5]), depth = atoi(argv[6]); double seed = atof(argv[7]);
 
+    /* create(0), or with BRT_MOCK_DEVICES="0,1,..." create([0, 1, ...]): one ctx spanning several GPUs */
     Val* a1[1] = { num(0) };
+    const char* devs = getenv("BRT_MOCK_DEVICES");
+    if (devs && *devs) {
+        Val* arr = mk(napi_object); arr->is_array = 1; arr->elems = (Val**)calloc(16, sizeof(Val*));
+        char* copy = strdup(devs);
+        for (char* tok = strtok(copy, ","); tok && arr->n_elems < 16; tok = strtok(NULL, ",")) arr->elems[arr->n_elems++] = num(atof(tok));
+        a1[0] = arr;
+    }
     Val* ctx = call(exports, "create", a1, 1);
     Val* js = mk(napi_string); js->str = text;
     Val* a4[4] = { ctx, js, num(W), num(H) };
@@ -168,8 +180,8 @@ int main(int argc, char** argv) {
     }
     Val* a5[1] = { ctx };
     Val* st = call(exports, "stats", a5, 1);
-    printf("render resolved; onProgress calls=%d last=%.3f; stats.samples=%.0f launches=%.0f\n", n_progress, last_progress,
-           find(st, "samples")->num, find(st, "launches")->num);
+    printf("render resolved; onProgress calls=%d last=%.3f; stats.samples=%.0f launches=%.0f devices=%.0f\n", n_progress, last_progress,
+           find(st, "samples")->num, find(st, "launches")->num, find(st, "devices")->num);
     FILE* o = fopen(argv[8], "wb"); if (!o) { perror(argv[8]); return 2; }
     fwrite(px->ta_data, 1, px->ta_len, o); fclose(o);
     return 0;

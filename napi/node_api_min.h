@@ -1,9 +1,9 @@
 /* Minimal declaration of the stable Node-API (N-API v4) surface used by brt_addon.c.
  *
- * The build image has no Node.js (no `node`, no node_api.h), so the addon is compiled against these prototypes as a
- * syntax / ABI check and cannot be loaded here.  With a Node toolchain present, brt_addon.c includes the real
- * <node_api.h> instead (see the __has_include test there) — the declarations below restate that header's C ABI for the
- * functions we call and nothing else. */
+ * The build image has no Node.js (no `node`, no node_api.h), so the addon is compiled against these prototypes; it is
+ * loaded and driven here by napi/mock_node_host.c, which implements them (tests/test_napi_mock.py).  With a Node toolchain
+ * present, brt_addon.c includes the real <node_api.h> instead (see the __has_include test there) — the declarations below
+ * restate that header's C ABI for the functions we call and nothing else. */
 #ifndef BRT_NODE_API_MIN_H
 #define BRT_NODE_API_MIN_H
 #include <stddef.h>
@@ -54,6 +54,9 @@ napi_status napi_get_value_string_utf8(napi_env env, napi_value value, char* buf
 napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type, size_t* length, void** data,
                                      napi_value* arraybuffer, size_t* byte_offset);
 napi_status napi_typeof(napi_env env, napi_value value, napi_valuetype* result);
+napi_status napi_is_array(napi_env env, napi_value value, bool* result);
+napi_status napi_get_array_length(napi_env env, napi_value value, uint32_t* result);
+napi_status napi_get_element(napi_env env, napi_value object, uint32_t index, napi_value* result);
 napi_status napi_create_object(napi_env env, napi_value* result);
 napi_status napi_create_int32(napi_env env, int32_t value, napi_value* result);
 napi_status napi_create_double(napi_env env, double value, napi_value* result);

@@ -11,8 +11,11 @@
 // putImageData is called, onProgress(fraction) fires and ends with 1.0, window.renderCancelled stops the render without
 // the final blit.  The image is written by the GPU directly into imageData.data's backing store.
 //
-// NOTE: this image has no Node.js, so this file and brt_addon.node have not been executed here; the same C ABI is
-// exercised end to end by the Python ctypes binding (blenderraytracer_b200/) and its tests.
+// NOTE: the build image has no Node.js, so this file (pure JavaScript) has not been executed there; brt_addon.node itself is
+// loaded and driven end to end by a mock N-API host (napi/mock_node_host.c, tests/test_napi_mock.py) and produces the same
+// bytes as the Python ctypes binding (blenderraytracer_b200/) of the same C ABI.
+//
+//   installGpuRender(RayTracer, { devices: [0, 1, 2, 3, 4, 5, 6, 7] })    // one ctx over 8 GPUs: render() is still ONE call
 import { createRequire } from 'node:module';
 const require = createRequire(import.meta.url);
 const addon = require('./brt_addon.node');
@@ -83,7 +86,7 @@ function backgroundOf(rt) {
   return { kind: 0, color: [0.1, 0.1, 0.1] };
 }
 
-export function installGpuRender(RayTracer, { device = 0, seed = 1 } = {}) {
+export function installGpuRender(RayTracer, { device = 0, devices = undefined, seed = 1, preview = true } = {}) {
   const origUpdateBackground = RayTracer.prototype.updateBackground;
   RayTracer.prototype.updateBackground = function (type, intensity = 1.0) {       // ray-tracer.js:568-585
     origUpdateBackground.call(this, type, intensity);
@@ -105,7 +108,7 @@ export function installGpuRender(RayTracer, { device = 0, seed = 1 } = {}) {
   };
 
   RayTracer.prototype.render = async function (onProgress) {                       // ray-tracer.js:166-281
-    this._brt ??= addon.create(device);
+    this._brt ??= addon.create(devices ?? device);                  // an array: brt_create_multi, samples split over the GPUs
     const ctx = this._brt;
     const flat = flattenWorld(this.world);
     addon.setSceneFlat(ctx, flat.objects, flat.materials, flat.tris, flat.lights, flat.textures, flat.perms);
@@ -118,10 +121,16 @@ export function installGpuRender(RayTracer, { device = 0, seed = 1 } = {}) {
       aaMode: this.antiAliasing in AA ? AA[this.antiAliasing] : 3, toneMapping: TONEMAP[this.toneMapping] ?? 0,
       exposure: this.exposure, gamma: this.gamma, denoising: this.denoising ? 1 : 0, denoiseStrength: this.denoiseStrength,
       seed: seed + (this._brtFrame = (this._brtFrame ?? 0) + 1),     // Math.random is unseeded: a new stream per render
+      // progressive preview: before every progress callback libbrt resolves the image of the samples traced so far into
+      // imageData.data, and the callback below blits it — the reference blits finished rows as it goes (:236-238)
+      preview: preview ? 1 : 0,
     });
     const poll = setInterval(() => { if (globalThis.window?.renderCancelled) addon.cancel(ctx); }, 50);   // :190,:256
     try {
-      await addon.render(ctx, this.imageData.data, onProgress);
+      await addon.render(ctx, this.imageData.data, (fraction) => {
+        if (preview && fraction < 1) this.ctx.putImageData(this.imageData, 0, 0);   // :236-238 (whole image of fewer samples instead of finished rows)
+        if (onProgress) onProgress(fraction);                                        // :258-259
+      });
     } catch (e) {
       if (e.code === 'BRT_E_CANCELLED') return;                      // the reference stops without the final blit (:264)
       throw e;

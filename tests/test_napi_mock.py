@@ -56,3 +56,15 @@ def test_addon_render_equals_python_binding(built, tmp_path):
     want = rt.render(onProgress=lambda f: None)
     assert np.array_equal(got, want)
     assert got[..., 3].min() == 255 and got[..., :3].std() > 10
+    # create([0]) / create([0, 1]): one context spanning the listed GPUs (brt_create_multi) behind the same render() call
+    import torch
+    for devs in (["0"], ["0", "1"]):
+        if len(devs) > torch.cuda.device_count():
+            continue
+        raw2 = tmp_path / f"o{len(devs)}.rgba"
+        out = subprocess.run([host, addon, scene, str(W), str(H), str(spp), str(depth), str(seed), str(raw2)], capture_output=True, text=True,
+                             timeout=300, env=dict(os.environ, BRT_MOCK_DEVICES=",".join(devs)))
+        assert out.returncode == 0, out.stderr
+        assert f"devices={len(devs)}" in out.stdout and "onProgress calls=4" in out.stdout
+        got2 = np.fromfile(raw2, dtype=np.uint8).reshape(H, W, 4)
+        assert np.abs(got2.astype(int) - want.astype(int)).max() <= (0 if len(devs) == 1 else 1)
