@@ -457,6 +457,11 @@ class OracleRayTracer:
         self.linear = None
         self.setupDefaultScene()
 
+    def setCloudPermutation(self, perm256):
+        """world.cloudNoise.p (noise.js:7-17): random per World in the reference, an explicit input here."""
+        self.perm = np.ascontiguousarray(np.asarray(perm256, dtype=np.uint8).reshape(256))
+        self.scene.set_perm(self.perm)
+
     # -- presets ------------------------------------------------------------------------------------
     def _new_world(self):
         self.scene = OracleScene()
