@@ -504,7 +504,11 @@ static __device__ __noinline__ bool refine_primary(const DevScene& sc, uint32_t 
         if (fabs(a) < 0.0001) return false;
         double f = __ddiv_rn(1.0, a);
         D3 sv = O - v0;
+        double u = __dmul_rn(f, dot(sv, h));
+        if (u < 0.0 || u > 1.0) return false;
         D3 qq = cross(sv, e1);
+        double v = __dmul_rn(f, dot(D, qq));
+        if (v < 0.0 || __dadd_rn(u, v) > 1.0) return false;
         t = __dmul_rn(f, dot(e2, qq));
         if (!(t >= tMin)) return false;
         n = normalize0(cross(e1, e2));
@@ -515,6 +519,61 @@ static __device__ __noinline__ bool refine_primary(const DevScene& sc, uint32_t 
     s.N = front ? tof3(n) : tof3(d3(-n.x, -n.y, -n.z));
     s.front = front;
     tOut = t;
+    return true;
+}
+
+// Primary visibility decided in float64 (the PRECISE instantiations: sampler = reference, the fp32 AOV kernel).  fp32 only
+// PROPOSES: the hierarchy is walked with fp32 slab tests on padded boxes (conservative: a box is ~100x wider than the rounding
+// of the ray and of the slab arithmetic), and EVERY primitive whose leaf is reached is evaluated by refine_primary — float64,
+// the reference's operation order, its root selection and thresholds — from the float64 camera ray.  The closest float64 hit
+// wins, exact ties go by the reference's loop order (tie_wins), and the fp32 cull distance is the float64 best widened by a
+// few ulps so a candidate at an equal distance is still visited.  The chosen primitive, its t, point and normal are therefore
+// the float64 reference's own (IDs bit-exact; tests/test_gpu_parity.py asserts zero mismatches against the brute-force
+// float64 kernel and the oracle), at the price of ~60 double-precision operations per candidate leaf of a PRIMARY ray.
+template <bool USE_BVH, bool HYBRID>
+static __device__ __noinline__ bool trace_primary64(const DevScene& sc, D3 O64, D3 D64, uint32_t* sstack, int sstride, uint32_t& pidOut,
+                                                    double& tOut, Surface& sfOut) {
+    double bestT = CUDART_INF; uint32_t bestPid = PID_NONE;
+    auto candidate = [&](uint32_t pid) {
+        Surface s; double t;
+        if (!refine_primary(sc, pid, O64, D64, t, s)) return;
+        if (t < bestT || (t == bestT && bestPid != PID_NONE && tie_wins(sc, pid, bestPid))) { bestT = t; bestPid = pid; sfOut = s; }
+    };
+    for (int i = 0; i < sc.nPln; i++) candidate(make_pid(PT_PLANE, i));
+    if (!USE_BVH || sc.nNodes == 0) {                                            // the reference's own linear loops, in float64
+        for (int i = 0; i < sc.nSph; i++) candidate(make_pid(PT_SPHERE, i));
+        for (int i = 0; i < sc.nBox; i++) candidate(make_pid(PT_BOX, i));
+        for (int i = 0; i < sc.nTri; i++) candidate(make_pid(PT_TRI, i));
+    } else {
+        const float3 O = tof3(O64), D = tof3(D64);
+        RayInv r = ray_inv(O, D);
+        uint32_t lstack[HYBRID ? LOCAL_STACK : 1];
+        int sp = 0;
+        uint32_t cur = 0;
+        for (;;) {
+            if (cur & LEAF_BIT) candidate(cur & ~LEAF_BIT);
+            else {
+                // cull distance: the float64 best, rounded up and widened (equal-distance candidates must still be reached)
+                const float tCull = bestT < 1e30 ? __fmul_rn(__double2float_ru(bestT), 1.000002f) + 1e-30f : CUDART_INF_F;
+                uint32_t nearc, farc; bool both;
+                if (node_visit(sc.nodes, cur, r, tCull, nearc, farc, both)) {
+                    if (both) {
+                        if (!HYBRID || sp < SMEM_STACK) sstack[sp * sstride] = farc; else lstack[sp - SMEM_STACK] = farc;
+                        sp++;
+                    }
+                    cur = nearc;
+                    continue;
+                }
+            }
+            if (sp == 0) break;
+            sp--;
+            cur = (!HYBRID || sp < SMEM_STACK) ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
+        }
+    }
+    if (bestPid == PID_NONE) return false;
+    int4 m = __ldg(&sc.meta[meta_index(sc, bestPid)]);
+    sfOut.objId = m.x; sfOut.matId = m.y; sfOut.triId = m.z;
+    pidOut = bestPid; tOut = bestT;
     return true;
 }
 

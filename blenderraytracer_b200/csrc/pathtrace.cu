@@ -66,18 +66,21 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 aliveMask = __activemask();
                 if (lane == __ffs(aliveMask) - 1) { cnt.mainIter++; cnt.mainLanes += __popc(aliveMask); }
             }
-            Hit h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
+            Hit h;
+            Surface sf;
+            if (PRECISE && depth == 0) {                                      // primary visibility decided in float64 (trace_primary64)
+                D3 O64, D64; double t64 = 0.0;
+                camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
+                if (COUNT) cnt.rays++;
+                h.pid = PID_NONE; h.t = CUDART_INF_F;
+                if (trace_primary64<USE_BVH, HYBRID>(sc, O64, D64, sstack, PT_BLOCK, h.pid, t64, sf)) h.t = (float)t64;
+            } else h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
             if (h.pid == PID_NONE) {                                          // ray-tracer.js:122
                 sum = sum + beta * background(sc, D);
                 alive = false;
                 continue;
             }
-            Surface sf = make_surface(sc, h, O, D, self);
-            if (PRECISE && depth == 0) {                                      // primary hit: float64 evaluation of the selected primitive
-                D3 O64, D64; double t64;
-                camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
-                refine_primary(sc, h.pid, O64, D64, t64, sf);
-            }
+            if (!(PRECISE && depth == 0)) sf = make_surface(sc, h, O, D, self);
             float4 m = ldg4(sc.mat + sf.matId);
             int mt = __ldg(sc.matType + sf.matId);
             if ((mt & 255) == 3) sum = sum + beta * (f3(m.x, m.y, m.z) * m.w);        // emitted (materials.js:95)
@@ -137,16 +140,12 @@ __global__ void __launch_bounds__(PT_BLOCK) k_primary_aov(const __grid_constant_
     CamSample cam = {};                                        // pixel centre, lens offset 0 (ray-tracer.js:144-147)
     D3 O64, D64;
     camera_ray64(p.cam, p.W, p.H, 0, col, jUp, cam, O64, D64);
-    float3 O = tof3(O64), D = tof3(D64);
-    Counters cnt;
-    Hit h = trace<USE_BVH, false, false>(p.sc, O, D, CUDART_INF_F, PID_NONE, cnt, smem_stack + threadIdx.x, PT_BLOCK);
+    uint32_t pid = PID_NONE; double t64 = 0.0; Surface sf;
+    const bool hit = trace_primary64<USE_BVH, true>(p.sc, O64, D64, smem_stack + threadIdx.x, PT_BLOCK, pid, t64, sf);   // the render path's own primary-hit code
     size_t k = (size_t)row * p.W + col;
-    if (h.pid == PID_NONE) {
+    if (!hit) {
         objId[k] = -1; triId[k] = -1; tOut[k] = CUDART_INF_F; nrm[3 * k] = nrm[3 * k + 1] = nrm[3 * k + 2] = 0.f; front[k] = 0;
     } else {
-        Surface sf = make_surface(p.sc, h, O, D, PID_NONE);
-        double t64 = (double)h.t;
-        refine_primary(p.sc, h.pid, O64, D64, t64, sf);           // the render path's own primary-hit code
         objId[k] = sf.objId; triId[k] = sf.triId; tOut[k] = (float)t64;
         nrm[3 * k] = sf.N.x; nrm[3 * k + 1] = sf.N.y; nrm[3 * k + 2] = sf.N.z; front[k] = sf.front ? 1 : 0;
     }

@@ -16,6 +16,7 @@ namespace brt {
 enum SlotField : int { F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_SELF, F_T, F_PID, F_BX, F_BY, F_BZ, F_STATE, F_RNGPOS };
 static_assert(F_RNGPOS == PT_SLOT_WORDS, "slot layout");
 constexpr int DEPTH_NEED_RAY = -1, DEPTH_DEAD = -2;
+constexpr uint32_t SELF_TRACED = 0x7FFFFFFEu;     // F_SELF marker: the slot's hit is already final (PRECISE primary rays are traced in float64 when armed)
 __host__ __device__ constexpr int slot_words(int sampler) { return PT_SLOT_WORDS + (sampler == 1 ? 1 : 0); }
 
 template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, int K>
@@ -63,14 +64,15 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
                 float3 D = f3(SLOT_F(F_DX, slot), SLOT_F(F_DY, slot), SLOT_F(F_DZ, slot));
                 float3 beta = f3(SLOT_F(F_BX, slot), SLOT_F(F_BY, slot), SLOT_F(F_BZ, slot));
                 Hit best; best.t = SLOT_F(F_T, slot); best.pid = SLOT_U(F_PID, slot);
-                const uint32_t self = SLOT_U(F_SELF, slot);
+                uint32_t self = SLOT_U(F_SELF, slot);
+                if (self == SELF_TRACED) self = PID_NONE;
                 if (SAMPLER == 1) rng.resume(pix, cs, SLOT_U(F_RNGPOS, slot), p.seedLo, p.seedHi);
                 bool cont = false;
                 if (best.pid == PID_NONE) {                                   // ray-tracer.js:122
                     sum = sum + beta * background(sc, D);
                 } else {
                     Surface sf = make_surface(sc, best, O, D, self);
-                    if (PRECISE && depth == 0) {                              // primary hit: float64 evaluation of the selected primitive
+                    if (PRECISE && depth == 0) {                              // primary hit: the float64 evaluation of the primitive trace_primary64 chose
                         D3 O64, D64; double t64;
                         RngSeq again;                                         // re-derive this path's camera sample (cheaper than 4 words per slot)
                         CamSample cam = camera_sample<SAMPLER>(p, pix, cs, again);
@@ -120,22 +122,30 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
                     cs = (uint32_t)s++;
                     CamSample cam = camera_sample<SAMPLER>(p, pix, cs, rng);
                     float3 O, D;
+                    uint32_t selfMark = PID_NONE;
                     if (PRECISE) {
+                        // primary visibility decided in float64, here and now (blocking; the extend-phase stacks are idle during
+                        // the shade phase): the slot is marked as traced and the extend phase passes it by
                         D3 O64, D64;
                         camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
                         O = tof3(O64); D = tof3(D64);
+                        uint32_t hp = PID_NONE; double t64 = 0.0; Surface tmp;
+                        if (COUNT) cnt.rays++;
+                        const bool hit = trace_primary64<USE_BVH, true>(sc, O64, D64, sstack, 32, hp, t64, tmp);
+                        SLOT_F(F_T, slot) = hit ? (float)t64 : CUDART_INF_F; SLOT_U(F_PID, slot) = hit ? hp : PID_NONE;
+                        selfMark = SELF_TRACED;
                     } else camera_ray32(p.cam32, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                     SLOT_F(F_OX, slot) = O.x; SLOT_F(F_OY, slot) = O.y; SLOT_F(F_OZ, slot) = O.z;
                     SLOT_F(F_DX, slot) = D.x; SLOT_F(F_DY, slot) = D.y; SLOT_F(F_DZ, slot) = D.z;
                     SLOT_F(F_BX, slot) = 1.f; SLOT_F(F_BY, slot) = 1.f; SLOT_F(F_BZ, slot) = 1.f;
-                    SLOT_U(F_SELF, slot) = PID_NONE;
+                    SLOT_U(F_SELF, slot) = selfMark;
                     if (SAMPLER == 1) SLOT_U(F_RNGPOS, slot) = rng.pos;
                     depth = 0;
                 } else depth = DEPTH_DEAD;
             }
             SLOT_U(F_STATE, slot) = (cs << 8) | (uint32_t)(depth + 2);
-            if (depth >= 0) {
-                alive = true;
+            if (depth >= 0) alive = true;
+            if (depth >= 0 && SLOT_U(F_SELF, slot) != SELF_TRACED) {
                 // arm the ray: unbounded planes (outside the BVH) are tested here, by the owner lane
                 if (COUNT) cnt.rays++;
                 float3 O = f3(SLOT_F(F_OX, slot), SLOT_F(F_OY, slot), SLOT_F(F_OZ, slot));
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS) k_pathtrace_wave(cons
                 if (next < NS && (__popc(idleMask) >= p.refill || idleMask == 0xffffffffu)) {
                     if (idx < 0) {
                         const int cand = next + __popc(idleMask & ((1u << lane) - 1u));
-                        if (cand < NS && (SLOT_U(F_STATE, cand) & 255u) >= 2u) {
+                        if (cand < NS && (SLOT_U(F_STATE, cand) & 255u) >= 2u && SLOT_U(F_SELF, cand) != SELF_TRACED) {
                             idx = cand;
                             O = f3(SLOT_F(F_OX, idx), SLOT_F(F_OY, idx), SLOT_F(F_OZ, idx));
                             D = f3(SLOT_F(F_DX, idx), SLOT_F(F_DY, idx), SLOT_F(F_DZ, idx));
