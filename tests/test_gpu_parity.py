@@ -627,3 +627,31 @@ def test_full_size_c5_crop_sample_for_sample(brt):
     lin_err = np.abs(rt.linearMean[y0:y1, x0:x1, :3] - o.linear[y0:y1, x0:x1, :3])
     assert np.median(lin_err) <= 1e-5
     assert ref[y0:y1, x0:x1, :3].std() > 1                # terrain, not a flat sky
+
+
+def test_full_size_c4_crop_statistical_parity(brt):
+    """BASELINE config 4 at its full 1920x1080, depth 16, procedural sky (Perlin clouds seen through the open front via the
+    mirror and the glass sphere): a crop of the frame traced by the oracle at 256 spp against the same crop of the GPU's full
+    frame (fast sampler, the benchmarked instantiation) — RMSE within 1.5x the oracle's own seed-to-seed RMSE, no bias."""
+    from oracle.oracle import OracleRayTracer
+    from tools import gen_scenes
+    scene = gen_scenes.cornell("procedural_sky")
+    W, H, spp, depth = 1920, 1080, 256, 16
+    x0, y0, x1, y1 = 1000, 700, 1128, 772                 # 128 x 72 px: mirror sphere, box edge and floor
+    rt = brt.RayTracer(W, H, seed=51, perm_seed=42)
+    assert rt.loadFromJSON(scene)
+    rt.updateRenderSettings(dict(samples=spp, maxBounces=depth))
+    rt.render()
+    g = rt.floatData[y0:y1, x0:x1, :3].astype(np.float64)
+    crops = []
+    for seed in (52, 53):
+        o = OracleRayTracer(W, H, seed=seed, threads=8, perm_seed=42)
+        assert o.loadFromJSON(scene)
+        o.updateRenderSettings(dict(samples=spp, maxBounces=depth))
+        o.render(rect=(x0, y0, x1, y1))
+        crops.append(o.floatData[y0:y1, x0:x1, :3].astype(np.float64))
+    a, b = crops
+    rmse, floor = np.sqrt(np.mean((g - a) ** 2)), np.sqrt(np.mean((b - a) ** 2))
+    assert rmse <= 1.5 * floor + 1e-4, (rmse, floor)
+    assert np.abs((g - a).mean(axis=(0, 1))).max() <= 4e-3 + 3 * np.abs((b - a).mean(axis=(0, 1))).max()
+    assert a.std() > 0.05                                 # the crop really contains geometry
