@@ -372,6 +372,7 @@ __device__ __forceinline__ bool node_visit(const float4* __restrict__ nodes, uin
     // conservative: boxes are inflated at build time and the far bound is widened by a few ulps (the slab arithmetic's
     // own error grows with the distance to the ray origin), so the BVH can only add candidates, never lose one the
     // brute-force loop would have found.
+    // (without the widening the 1 M-triangle terrain loses hits the linear loop finds — measured, tools/ab.py — so it stays)
     bool h0 = tn0 <= __fmul_rn(tf0, 1.0000005f), h1 = tn1 <= __fmul_rn(tf1, 1.0000005f);
     bool swap = tn1 < tn0;
     both = h0 & h1;
@@ -390,9 +391,12 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
     if (sc.nNodes == 0) return best;
     RayInv r = ray_inv(O, D);
-    uint32_t lstack[HYBRID ? LOCAL_STACK : 1];
     int sp = 0;
     uint32_t cur = 0;
+    uint32_t lstack[HYBRID ? LOCAL_STACK : 1];
+    // (A variant with a uniform tail — far child stored unconditionally, "pop" as a select on a stack top that every lane
+    // loads each iteration — removed the divergent pop block, 6-8 % of issued instructions at 6-7 lanes, but put a shared-memory
+    // load on every iteration's critical path: C3 -2.8 %, C5 -0.9 %, C4 +3.3 % on a B200.  The branchy form stays.)
     for (;;) {
         if (COUNT && !SHADOW) {
             // lane attribution: which lanes of the warp execute this iteration, and doing what (profiles/*lane_attribution*)
@@ -718,11 +722,22 @@ __device__ inline float3 texture_value(const DevScene& sc, int ti, float3 P) {
 
 // ------------------------------------------------------------------------------------------- sampling
 // math.js:22-31 by direct inversion (identical distributions; used by BRT_SAMPLER_FAST).
+// sin / cos of 2*pi*u for the FAST sampler's random angles: the MUFU approximations (absolute error ~2^-21 on [0, 2 pi)) in
+// place of the ~40-instruction exact sincospif — these angles are uniform random numbers, so the error is far below the
+// Monte-Carlo noise floor and unbiased; the reference sampler keeps sincospif (compared sample for sample with the oracle).
+__device__ __forceinline__ void fast_sincos2pi(float u, float* sn, float* cs) {
+#ifndef BRT_EXACT_SINCOS
+    const float x = __fmul_rn(6.283185307179586f, u);
+    *sn = __sinf(x); *cs = __cosf(x);                      // +3 % on C3 / C4, +4 % on C2 (B200, tools/ab.py)
+#else
+    sincospif(__fmul_rn(2.f, u), sn, cs);
+#endif
+}
 __device__ __forceinline__ float3 uniform_sphere(float u0, float u1) {
     float z = fmaf(-2.f, u0, 1.f);
     float r = sqrtf(fmaxf(0.f, fmaf(-z, z, 1.f)));
     float sn, cs;
-    sincospif(__fmul_rn(2.f, u1), &sn, &cs);
+    fast_sincos2pi(u1, &sn, &cs);
     return f3(__fmul_rn(r, cs), __fmul_rn(r, sn), z);
 }
 

@@ -55,7 +55,7 @@ __device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t p
         uint4 r = philox_fast(pix, s, 0u, PHILOX_TAG, p.seedLo, p.seedHi);
         a0 = u01(r.x); a1 = u01(r.y);
         float rr = sqrtf(u01(r.z)), sn, cs_;                   // unit disk by inversion (math.js:27-31 distribution)
-        sincospif(__fmul_rn(2.f, u01(r.w)), &sn, &cs_);
+        fast_sincos2pi(u01(r.w), &sn, &cs_);
         cs.dx = __fmul_rn(rr, cs_); cs.dy = __fmul_rn(rr, sn);
     } else {
         rng.init(pix, s, p.seedLo, p.seedHi);
@@ -65,7 +65,7 @@ __device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t p
     if (p.aaMode == 1) { cs.s = a0; cs.t = a1; }
     else if (p.aaMode == 2) {                                    // stochastic: disk of radius 0.5 about the pixel centre
         float sr = sqrtf(a0), sn, c2;
-        sincospif(__fmul_rn(2.f, a1), &sn, &c2);
+        if (SAMPLER == 0) fast_sincos2pi(a1, &sn, &c2); else sincospif(__fmul_rn(2.f, a1), &sn, &c2);
         cs.s = __fmul_rn(sr, c2); cs.t = __fmul_rn(sr, sn);
     }
     return cs;

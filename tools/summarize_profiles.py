@@ -80,28 +80,54 @@ def ncu_summary(rep, dst, title):
         f.write(sass_hist(rep) + "\n")
     return m
 
+def sass_loop_excerpt(dst):
+    """A trimmed cuobjdump -sass listing of the hot kernel's node-visit block (LDG.E.128 node loads, FFMA slabs, FMNMX / FMNMX3)."""
+    obj = os.path.join(ROOT, "blenderraytracer_b200", "csrc", "build", "pathtrace.o")
+    fn = "_ZN3brt16k_pathtrace_megaILi0ELb1ELb0ELb0ELb0ELi1EEEvNS_8PTParamsE"
+    txt = subprocess.check_output(["cuobjdump", "-sass", "-fun", fn, obj], text=True)
+    lines = [l for l in txt.splitlines() if "/*" in l and not l.strip().startswith("/* 0x")]
+    lines = [l.split("/* 0x")[0].rstrip() for l in lines]
+    ix = [i for i, l in enumerate(lines) if "FMNMX3" in l]
+    lo = max(0, ix[0] - 40)
+    while lo < ix[0] and "LDG.E.128" not in lines[lo]:
+        lo += 1
+    hi = min(len(lines), ix[-1] + 30)
+    with open(dst, "w") as f:
+        f.write("# cuobjdump -sass of k_pathtrace_mega<fast, bvh, PRIMS_SPHERE> (sm_100a): the node-visit block of the traversal loop\n"
+                "# (four 128-bit read-only loads of the 64-byte node, 12 FFMA slab planes, FMNMX / FMNMX3 reductions, near / far select, shared-memory push)\n")
+        f.write("\n".join(lines[max(0, lo - 3):hi]) + "\n")
+
+
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     if os.path.exists(os.path.join(G, "launches_c3_spp16.csv")):
         launches(os.path.join(G, "launches_c3_spp16.csv"), os.path.join(P, f"{R}_launches_c3_spp16.csv"))
-    for rep, name, title in (("prof_c3_mega.ncu-rep", "ncu_k_pathtrace_mega_c3_spp16", "k_pathtrace_mega<fast, bvh> on C3 (1920x1080 random spheres) at 16 spp"),
-                             ("prof_c3_k3.ncu-rep", "ncu_k_pathtrace_wave_k3_c3_spp16", "k_pathtrace_wave (warp-local wavefront, 3 paths in flight per lane, 19-word slots) on C3 at 16 spp")):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from source_hist import hist
+    for rep, name, title, tag in ((f"{R}_prof_c3_mega.ncu-rep", "ncu_k_pathtrace_mega_c3_spp16", "k_pathtrace_mega<fast, bvh, spheres> on C3 (1920x1080 random spheres) at 16 spp", "c3"),
+                                  (f"{R}_prof_c5_mega.ncu-rep", "ncu_k_pathtrace_mega_c5_spp16", "k_pathtrace_mega<fast, bvh, triangles> on C5 (1 M-triangle terrain, 3840x2160) at 16 spp", "c5")):
         src = os.path.join(G, rep)
-        if os.path.exists(src):
-            m = ncu_summary(src, os.path.join(P, f"{R}_{name}.txt"), title)
-            if "mega" in rep:
-                def b(k):
-                    u, v = m[k]; v = float(v)
-                    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-                tr = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
-                json.dump({"kernel": "k_pathtrace_mega", "dram_bytes_per_launch": tr, "dram_bytes_read": b("dram__bytes_read.sum"),
-                           "dram_bytes_write": b("dram__bytes_write.sum"),
-                           "note": "ncu --set full, one launch of the C3 bench at 16 spp; the traffic is the W*H*16 B accumulation buffer read + write "
-                                   "(the L2 was flushed before the launch) plus scene data once, so it does not grow with spp"},
-                          open(os.path.join(P, "traffic_c3.json"), "w"), indent=1)
+        if not os.path.exists(src):
+            continue
+        m = ncu_summary(src, os.path.join(P, f"{R}_{name}.txt"), title)
+        with open(os.path.join(P, f"{R}_source_hist_{tag}.txt"), "w") as f:
+            f.write(f"# {title}: warp-level instructions by CUDA source line (ncu --page source --print-source cuda,sass), hottest 60\n" + hist(src, 60) + "\n")
+        def b(k):
+            u, v = m[k]; v = float(v)
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        tr = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
+        json.dump({"kernel": "k_pathtrace_mega", "dram_bytes_per_launch": tr, "dram_bytes_read": b("dram__bytes_read.sum"),
+                   "dram_bytes_write": b("dram__bytes_write.sum"),
+                   "note": f"ncu --set full, one launch of the {tag.upper()} bench at 16 spp; the traffic is the W*H*16 B accumulation buffer read + write "
+                           "(the L2 was flushed before the launch) plus scene data, so it does not grow with spp"},
+                  open(os.path.join(P, f"traffic_{tag}.json"), "w"), indent=1)
+    try:
+        sass_loop_excerpt(os.path.join(P, f"{R}_sass_node_visit.txt"))
+    except Exception as ex:
+        print("sass excerpt failed:", ex)
     for f in sorted(os.listdir(G)):
         if f.startswith("bench_") and f.endswith(".json"):
             txt = open(os.path.join(G, f)).read().strip().splitlines()
             if txt:
                 open(os.path.join(P, f"{R}_{f}"), "w").write(txt[-1] + "\n")
-    print(os.listdir(P))
+    print(sorted(os.listdir(P)))
