@@ -79,7 +79,7 @@ export function buildCase(ref, c) {
     toneMapping: c.tonemap ?? 'reinhard', antiAliasing: c.aa ?? 'supersampling', denoising: !!c.denoise, denoiseStrength: c.strength ?? 0.5 });
   const bg = c.scene?.background;
   if (bg && (bg.type === 'solid' || bg.type === 'hdri')) {
-    // Deviation D1 (INTEGRATION.md §5): js/scene-loader.js:43,45 bind the background FACTORY instead of calling it, so the
+    // Deviation D1 (INTEGRATION.md §6): js/scene-loader.js:43,45 bind the background FACTORY instead of calling it, so the
     // loaded world returns a function where a colour is expected (NaN -> black) until the UI re-installs the background
     // (ui-controller.js:181).  The oracle and libbrt implement the intended behaviour; the harness installs it the way
     // ray-tracer.js:573-576 does, honouring the JSON colour.

@@ -44,46 +44,61 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
         float3 sum = f3(0.f, 0.f, 0.f), beta = f3(1.f, 1.f, 1.f), O = f3(0, 0, 0), D = f3(0, 0, 1);
         uint32_t self = PID_NONE, cs = 0;
         int depth = 0;
-        bool alive = false;
-        CamSample cam = {};
+        bool alive = false;                                                   // true: the lane holds a hit to scatter from
+        Surface sf = {};                                                      // that hit (kept across the back edge only, not across trace)
+        uint32_t hitPid = PID_NONE;
         RngSeq rng;
         uint32_t* sstack = smem + threadIdx.x;
         if (p.maxDepth <= 0) s = sEnd;                                        // rayColor(depth <= 0) is black (ray-tracer.js:103): only alpha moves
+        // One iteration = [draw] -> [start a path: camera ray | continue one: scatter at the previous hit] -> trace -> [miss:
+        // background | hit: surface + emission].  The lanes that start a path and the lanes that continue one draw their
+        // Philox block in the SAME call (counter block 0 / block depth): one full-warp instance of the generator instead of
+        // two half-empty ones.
         for (;;) {
             if (!alive) {
                 if (s >= sEnd) break;
                 cs = (uint32_t)s++;
-                cam = camera_sample<SAMPLER>(p, pix, cs, rng);
-                if (PRECISE) {
-                    D3 O64, D64;
+                depth = 0;
+            }
+            uint4 r = make_uint4(0u, 0u, 0u, 0u);
+            if (SAMPLER == 0) r = philox_fast(pix, cs, (uint32_t)depth, PHILOX_TAG, p.seedLo, p.seedHi);
+            Hit h;
+            bool primaryDone = false;
+            if (!alive) {
+                CamSample cam = camera_sample_drawn<SAMPLER>(p, r, pix, cs, rng);
+                if (PRECISE) {                                                // primary visibility decided in float64 (trace_primary64)
+                    D3 O64, D64; double t64 = 0.0;
                     camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
                     O = tof3(O64); D = tof3(D64);
+                    if (COUNT) cnt.rays++;
+                    h.pid = PID_NONE; h.t = CUDART_INF_F;
+                    if (trace_primary64<USE_BVH, HYBRID>(sc, O64, D64, sstack, PT_BLOCK, h.pid, t64, sf)) h.t = (float)t64;
+                    primaryDone = true;
                 } else camera_ray32(p.cam32, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
-                beta = f3(1.f, 1.f, 1.f); self = PID_NONE; depth = 0; alive = true;
+                beta = f3(1.f, 1.f, 1.f); self = PID_NONE;
+            } else {
+                float4 m = ldg4(sc.mat + sf.matId);
+                int mt = __ldg(sc.matType + sf.matId);
+                float3 Dn, att;
+                if (!scatter_drawn<SAMPLER>(p, mt, m, sf, D, r, rng, Dn, att)) { alive = false; continue; }   // absorbed (metal below the horizon)
+                beta = beta * att;
+                O = sf.P; D = Dn; self = hitPid;
             }
+            alive = false;
             unsigned aliveMask = 0xffffffffu;
             if (COUNT) {
                 aliveMask = __activemask();
                 if (lane == __ffs(aliveMask) - 1) { cnt.mainIter++; cnt.mainLanes += __popc(aliveMask); }
             }
-            Hit h;
-            Surface sf;
-            if (PRECISE && depth == 0) {                                      // primary visibility decided in float64 (trace_primary64)
-                D3 O64, D64; double t64 = 0.0;
-                camera_ray64(p.cam, p.W, p.H, p.aaMode, col, jUp, cam, O64, D64);
-                if (COUNT) cnt.rays++;
-                h.pid = PID_NONE; h.t = CUDART_INF_F;
-                if (trace_primary64<USE_BVH, HYBRID>(sc, O64, D64, sstack, PT_BLOCK, h.pid, t64, sf)) h.t = (float)t64;
-            } else h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
+            if (!(PRECISE && primaryDone)) h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
             if (h.pid == PID_NONE) {                                          // ray-tracer.js:122
                 sum = sum + beta * background(sc, D);
-                alive = false;
                 continue;
             }
-            if (!(PRECISE && depth == 0)) sf = make_surface(sc, h, O, D, self);
+            if (!(PRECISE && primaryDone)) sf = make_surface(sc, h, O, D, self);
             float4 m = ldg4(sc.mat + sf.matId);
             int mt = __ldg(sc.matType + sf.matId);
-            if ((mt & 255) == 3) sum = sum + beta * (f3(m.x, m.y, m.z) * m.w);        // emitted (materials.js:95)
+            if ((mt & 255) == 3) { sum = sum + beta * (f3(m.x, m.y, m.z) * m.w); continue; }   // emitted, no scatter (materials.js:94-95)
             if (DIRECT && (mt & 255) == 0) {
                 // EXTENSION (off by default): lights.js:22-47 give direction / colour / distance.
                 for (int li = 0; li < sc.nLights; li++) {
@@ -102,12 +117,10 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                     sum = sum + beta * (f3(m.x, m.y, m.z) * lcol) * cosN;
                 }
             }
-            float3 Dn, att;
-            bool cont = scatter<SAMPLER>(p, mt, m, sf, D, pix, cs, depth, rng, Dn, att);
             depth++;
-            if (!cont || depth >= p.maxDepth) { alive = false; continue; }   // depth <= 0 returns black (ray-tracer.js:103)
-            beta = beta * att;
-            O = sf.P; D = Dn; self = h.pid;
+            if (depth >= p.maxDepth) continue;                                // the next ray would return black (ray-tracer.js:103): at most maxDepth intersections
+            hitPid = h.pid;
+            alive = true;                                                     // scatter at the top of the next iteration (sf, D = incoming direction)
         }
         // each z chunk owns its own plane of the accumulation target (planeStride = 0 when there is one chunk):
         // no atomics, so the sum is deterministic; k_sum_planes folds the planes in fixed order afterwards

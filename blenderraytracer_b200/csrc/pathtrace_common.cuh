@@ -47,12 +47,13 @@ __device__ __forceinline__ void camera_ray32(const DevCamera32& c, int W, int H,
     if (c.type == 1) D = normalize0(D - f3(c.cw[0], c.cw[1], c.cw[2]));
 }
 
+// `r` = the Philox block (pixel, sample, 0) of the fast sampler, drawn by the caller (the megakernel draws the camera block of
+// the lanes that start a path and the scatter block of the lanes that continue one in ONE call: both are the same code).
 template <int SAMPLER>
-__device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t pix, uint32_t s, RngSeq& rng) {
+__device__ __forceinline__ CamSample camera_sample_drawn(const PTParams& p, uint4 r, uint32_t pix, uint32_t s, RngSeq& rng) {
     CamSample cs; cs.s = 0.f; cs.t = 0.f;
     float a0 = 0.f, a1 = 0.f;
     if (SAMPLER == 0) {
-        uint4 r = philox_fast(pix, s, 0u, PHILOX_TAG, p.seedLo, p.seedHi);
         a0 = u01(r.x); a1 = u01(r.y);
         float rr = sqrtf(u01(r.z)), sn, cs_;                   // unit disk by inversion (math.js:27-31 distribution)
         fast_sincos2pi(u01(r.w), &sn, &cs_);
@@ -70,18 +71,22 @@ __device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t p
     }
     return cs;
 }
+template <int SAMPLER>
+__device__ __forceinline__ CamSample camera_sample(const PTParams& p, uint32_t pix, uint32_t s, RngSeq& rng) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (SAMPLER == 0) r = philox_fast(pix, s, 0u, PHILOX_TAG, p.seedLo, p.seedHi);
+    return camera_sample_drawn<SAMPLER>(p, r, pix, s, rng);
+}
 
 // ------------------------------------------------------------------------------------------- materials (materials.js)
 // Returns false when the path ends here (emissive, absorbed metal).  `att` multiplies the throughput.
+// `r` = the Philox block (pixel, sample, bounce + 1) of the fast sampler, drawn by the caller (see camera_sample_drawn).
 template <int SAMPLER>
-__device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m, const Surface& sf, float3 Din, uint32_t pix,
-                                        uint32_t s, int bounce, RngSeq& rng, float3& Dout, float3& att) {
+__device__ __forceinline__ bool scatter_drawn(const PTParams& p, int matWord, float4 m, const Surface& sf, float3 Din, uint4 r,
+                                              RngSeq& rng, float3& Dout, float3& att) {
     const int matType = matWord & 255, tex = matWord >> 8;           // 1-based texture index above the type (materials.js:99-126)
     float u0 = 0.f, u1 = 0.f, u2 = 0.f;
-    if (SAMPLER == 0) {
-        uint4 r = philox_fast(pix, s, (uint32_t)(bounce + 1), PHILOX_TAG, p.seedLo, p.seedHi);
-        u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z);
-    }
+    if (SAMPLER == 0) { u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z); }
     if (matType == 0) {                                                       // Lambertian (materials.js:20-25)
         float3 unit;
         if (SAMPLER == 0) unit = uniform_sphere(u0, u1);
@@ -126,6 +131,13 @@ __device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m
         return true;
     }
     return false;                                                             // Emissive (materials.js:94)
+}
+template <int SAMPLER>
+__device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m, const Surface& sf, float3 Din, uint32_t pix,
+                                        uint32_t s, int bounce, RngSeq& rng, float3& Dout, float3& att) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (SAMPLER == 0) r = philox_fast(pix, s, (uint32_t)(bounce + 1), PHILOX_TAG, p.seedLo, p.seedHi);
+    return scatter_drawn<SAMPLER>(p, matWord, m, sf, Din, r, rng, Dout, att);
 }
 
 template <bool USE_BVH, bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY>
