@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include "brt_ctx.hpp"
 
@@ -17,6 +18,24 @@ int fail(brt_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; re
 int cuda_fail(brt_ctx* c, cudaError_t e, const char* where) {
     return fail(c, BRT_E_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
+}
+
+// Host-side work over large meshes (float64 -> fp32 flattening, the defensive copy of a borrowed mesh) is split over a few
+// threads: at 1 M triangles it is otherwise the largest part of a scene (re)load (25 ms single-threaded vs 3 ms of DMA).
+template <class F>
+static void parallel_chunks(size_t n, size_t minPerThread, F fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = hw ? hw : 1;
+    if (nt > 8) nt = 8;
+    if (n / (minPerThread ? minPerThread : 1) < nt) nt = n / (minPerThread ? minPerThread : 1);
+    if (nt <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (size_t k = 0; k < nt; k++) {
+        const size_t lo = k * per, hi = lo + per < n ? lo + per : n;
+        if (lo < hi) th.emplace_back([=] { fn(lo, hi); });
+    }
+    for (std::thread& t : th) t.join();
 }
 
 static void default_params(brt_render_params& p) {                 // ray-tracer.js:19-30
@@ -102,13 +121,13 @@ int brt_stream_synchronize(brt_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------- scene
-static int validate_scene(brt_ctx* ctx, const HostScene& s) {
+static int validate_scene(brt_ctx* ctx, const HostScene& s, uint64_t nMeshTris = ~0ull) {
     for (size_t i = 0; i < s.objects.size(); i++) {
         const brt_object& o = s.objects[i];
         if (o.type < BRT_OBJ_SPHERE || o.type > BRT_OBJ_MESH) return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": bad type");
         if (o.material < 0 || (size_t)o.material >= s.materials.size()) return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": bad material index");
         if (o.type == BRT_OBJ_MESH) {
-            const uint64_t nT = s.meshTris.size() / 9;              // no arithmetic on the untrusted values: nothing can wrap
+            const uint64_t nT = nMeshTris != ~0ull ? nMeshTris : s.meshTris.size() / 9;   // no arithmetic on the untrusted values: nothing can wrap
             if (o.first_tri < 0 || o.tri_count < 0 || (uint64_t)o.first_tri > nT || (uint64_t)o.tri_count > nT - (uint64_t)o.first_tri)
                 return fail(ctx, BRT_E_INVALID, "object " + std::to_string(i) + ": mesh triangle range out of bounds");
         }
@@ -157,7 +176,6 @@ int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {
     sc.materials.assign(d->materials, d->materials + d->n_materials);
     sc.lights.assign(d->lights, d->lights + d->n_lights);
     if (d->n_textures) sc.textures.assign(d->textures, d->textures + d->n_textures);
-    sc.meshTris.assign(d->mesh_triangles, d->mesh_triangles + 9 * (size_t)d->n_mesh_triangles);
     for (brt_object& o : sc.objects) if (o.type == BRT_OBJ_PLANE) {               // geometry.js:52
         double l = std::sqrt(o.b[0] * o.b[0] + o.b[1] * o.b[1] + o.b[2] * o.b[2]);
         if (l > 0) { o.b[0] /= l; o.b[1] /= l; o.b[2] /= l; } else o.b[0] = o.b[1] = o.b[2] = 0;
@@ -167,8 +185,18 @@ int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {
         double n = std::sqrt(l.v[0] * l.v[0] + l.v[1] * l.v[1] + l.v[2] * l.v[2]);
         if (n > 0) { l.v[0] /= n; l.v[1] /= n; l.v[2] /= n; } else l.v[0] = l.v[1] = l.v[2] = 0;
     }
-    int rc = validate_scene(ctx, sc);
-    if (rc != BRT_OK) return rc;
+    int rc = validate_scene(ctx, sc, (uint64_t)d->n_mesh_triangles);
+    if (rc != BRT_OK) return rc;                                    // the previous scene stays in place
+    // the mesh triangles (72 B each) are copied last, in parallel, into the ctx's own buffer: re-sending a scene of the same
+    // size touches no allocator (a fresh 72 MB vector costs more in page faults than the copy itself)
+    std::vector<double> keep;
+    keep.swap(ctx->scene.meshTris);
+    keep.resize(9 * (size_t)d->n_mesh_triangles);
+    {
+        const double* src = d->mesh_triangles; double* dst = keep.data();
+        parallel_chunks(9 * (size_t)d->n_mesh_triangles, 1u << 20, [=](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, (hi - lo) * sizeof(double)); });
+    }
+    sc.meshTris.swap(keep);
     ctx->scene = std::move(sc); ctx->haveScene = true; ctx->sceneDirty = true; ctx->obj64Dirty = true; ctx->sceneVersion++;
     return BRT_OK;
 }
@@ -226,11 +254,24 @@ static int upload_scene(brt_ctx* ctx) {
         case BRT_OBJ_PLANE: pln[2 * iP] = f4(o.b[0], o.b[1], o.b[2], 0); pln[2 * iP + 1] = f4(o.a[0], o.a[1], o.a[2], 0); meta[d.basePln + iP] = make_int4(obj, o.material, -1, 0); iP++; break;
         case BRT_OBJ_BOX: box[2 * iB] = f4(o.a[0], o.a[1], o.a[2], 0); box[2 * iB + 1] = f4(o.b[0], o.b[1], o.b[2], 0); meta[d.baseBox + iB] = make_int4(obj, o.material, -1, 0); iB++; break;
         case BRT_OBJ_TRIANGLE: put_tri(o.a, o.b, o.c, obj, o.material, -1); break;
-        default:
-            for (int64_t t = 0; t < o.tri_count; t++) {
-                const double* p = &s.meshTris[9 * (size_t)(o.first_tri + t)];
-                put_tri(p, p + 3, p + 6, obj, o.material, (int)t);
-            }
+        default: {
+            // a mesh: its triangles are independent rows of the SoA arrays, filled in parallel
+            const size_t base = iT, first = (size_t)o.first_tri;
+            const int mat_ = o.material;
+            const int baseTri = d.baseTri;
+            const double* src = s.meshTris.data();
+            parallel_chunks((size_t)o.tri_count, 65536, [=](size_t lo, size_t hi) {
+                for (size_t t = lo; t < hi; t++) {
+                    const double* p = src + 9 * (first + t);
+                    float4* q = tri + 3 * (base + t);
+                    q[0] = f4(p[0], p[1], p[2], 0);
+                    q[1] = f4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0);
+                    q[2] = f4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0);
+                    meta[baseTri + base + t] = make_int4(obj, mat_, (int)t, 0);
+                }
+            });
+            iT += (size_t)o.tri_count;
+        }
         }
     }
     // material type in the low byte, 1-based texture index above it (TexturedLambertian / TexturedMetal)
