@@ -33,12 +33,14 @@ def main():
     specs = sys.argv[1:] or ["c3:256", "c5:64", "c4:64", "c2:64"]
     out = []
     for spec in specs:
-        name, spp = spec.split(":")
+        name, spp = spec.split(":")[:2]
         spp = int(spp)
-        w = load_workload(name)
+        w = load_workload(name, binary=True)
+        if len(spec.split(":")) > 2:
+            w["depth"] = int(spec.split(":")[2])           # c5:64:1 = primary rays only
         W, H = w["W"], w["H"]
         rt = brt.RayTracer(W, H, device=0, seed=1)
-        assert rt.loadFromJSON(json.dumps(w["scene"]).encode())
+        assert rt.loadFromJSON(w.get("blob") or json.dumps(w["scene"]).encode())
         rt.resizeCanvas(W, H)
         rt.updateRenderSettings(dict(samples=spp, maxBounces=w["depth"]))
         rt.directLighting = bool(w.get("direct"))
@@ -55,7 +57,7 @@ def main():
             rt.synchronize()
             st = rt.stats()
             slots = 32 * st["trav_warp_iters"]
-            row = dict(workload=name, spp=spp, schedule=sched, kernel_ms=ms, msamples_s=W * H * spp / ms / 1e3,
+            row = dict(workload=name + (":d%d" % w["depth"]), spp=spp, schedule=sched, kernel_ms=ms, msamples_s=W * H * spp / ms / 1e3,
                        rays=st["rays"], rays_per_sample=st["rays"] / (W * H * spp),
                        node_visits_per_ray=st["tests_aabb"] / 2 / max(1, st["rays"]),
                        trav_warp_iters=st["trav_warp_iters"],
