@@ -65,14 +65,15 @@ class brt_render_params(C.Structure):
                 ("aa_mode", C.c_int32), ("tonemap", C.c_int32), ("exposure", C.c_double), ("gamma", C.c_double),
                 ("denoise", C.c_int32), ("_pad0", C.c_int32), ("denoise_strength", C.c_double), ("seed", C.c_uint64),
                 ("direct_lighting", C.c_int32), ("sampler", C.c_int32), ("integrator", C.c_int32), ("accel", C.c_int32),
-                ("spp_batch", C.c_int32), ("count_tests", C.c_int32), ("refill_threshold", C.c_int32), ("paths_in_flight", C.c_int32), ("preview", C.c_int32), ("_pad1", C.c_int32)]
+                ("spp_batch", C.c_int32), ("count_tests", C.c_int32), ("refill_threshold", C.c_int32), ("paths_in_flight", C.c_int32), ("preview", C.c_int32), ("bvh_width", C.c_int32)]
 
 
 class brt_scene_info(C.Structure):
     _fields_ = [("n_objects", C.c_int32), ("n_materials", C.c_int32), ("n_lights", C.c_int32),
                 ("n_spheres", C.c_int32), ("n_planes", C.c_int32), ("n_boxes", C.c_int32),
-                ("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("bvh_depth", C.c_int32), ("_pad", C.c_int32),
-                ("bvh_build_ms", C.c_double), ("upload_ms", C.c_double), ("upload_bytes", C.c_int64)]
+                ("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("bvh_depth", C.c_int32), ("bvh_width", C.c_int32),
+                ("bvh_build_ms", C.c_double), ("upload_ms", C.c_double), ("upload_bytes", C.c_int64),
+                ("bvh_wide_depth", C.c_int32), ("_pad", C.c_int32), ("bvh_wide_build_ms", C.c_double)]
 
 
 class brt_stats(C.Structure):
@@ -82,7 +83,7 @@ class brt_stats(C.Structure):
                 ("kernel_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double), ("launches", C.c_uint64),
                 ("trav_warp_iters", C.c_uint64), ("trav_lane_iters", C.c_uint64), ("trav_alive_lanes", C.c_uint64),
                 ("trav_node_issues", C.c_uint64), ("trav_leaf_issues", C.c_uint64), ("trav_leaf_lanes", C.c_uint64),
-                ("path_warp_iters", C.c_uint64), ("path_lane_iters", C.c_uint64)]
+                ("path_warp_iters", C.c_uint64), ("path_lane_iters", C.c_uint64), ("node_visits", C.c_uint64)]
 
 
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_double, C.c_void_p)

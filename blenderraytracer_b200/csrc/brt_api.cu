@@ -298,13 +298,15 @@ static int upload_scene(brt_ctx* ctx) {
     d.prim64 = nullptr; ctx->prim64Dirty = true;
     auto t1 = std::chrono::steady_clock::now();
     // the LBVH over the bounded primitives is built on first use (ensure_bvh): tiny scenes render with the linear loop
-    d.nodes = nullptr; d.nNodes = 0; d.bvhStackDepth = 0;
+    d.nodes = nullptr; d.cnodes = nullptr; d.nNodes = 0; d.bvhStackDepth = 0;
+    d.wnodes = nullptr; d.wideN = 0; d.wideDepth = 0; d.wideAxes = 0;
+    ctx->bin = BvhBuildResult{}; ctx->wide = WideBuildResult{};
     ctx->nBounded = d.nSph + d.nBox + d.nTri;
     ctx->bvhDirty = true;
     brt_scene_info& inf = ctx->info;
     inf.n_objects = (int)s.objects.size(); inf.n_materials = (int)nMat; inf.n_lights = (int)nLights;
     inf.n_spheres = d.nSph; inf.n_planes = d.nPln; inf.n_boxes = d.nBox; inf.n_triangles = d.nTri;
-    inf.n_bvh_nodes = 0; inf.bvh_depth = 0; inf.bvh_build_ms = 0;
+    inf.n_bvh_nodes = 0; inf.bvh_depth = 0; inf.bvh_build_ms = 0; inf.bvh_width = 0; inf.bvh_wide_depth = 0; inf.bvh_wide_build_ms = 0;
     inf.upload_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     inf.upload_bytes = (int64_t)arenaBytes;
     ctx->sceneDirty = false;
@@ -346,9 +348,38 @@ static int ensure_bvh(brt_ctx* ctx) {
     BvhBuildResult br{};
     CK(build_lbvh(ctx->dev, &ctx->bvhWs, &br, ctx->stream));
     if (br.depth > SMEM_STACK + LOCAL_STACK) return fail(ctx, BRT_E_STATE, "LBVH deeper than the traversal stack (" + std::to_string(br.depth) + ")");
-    ctx->dev.nodes = br.nodes; ctx->dev.nNodes = (int)br.nNodes; ctx->dev.bvhStackDepth = br.depth;
+    ctx->dev.nodes = br.nodes; ctx->dev.cnodes = br.cnodes; ctx->dev.nNodes = (int)br.nNodes; ctx->dev.bvhStackDepth = br.depth;
     ctx->info.n_bvh_nodes = br.nNodes; ctx->info.bvh_depth = br.depth; ctx->info.bvh_build_ms = br.buildMs;
+    ctx->bin = br; ctx->wide = WideBuildResult{};
+    ctx->dev.wnodes = nullptr; ctx->dev.wideN = 0; ctx->dev.wideDepth = 0; ctx->dev.wideAxes = 0;
+    ctx->info.bvh_width = 2; ctx->info.bvh_wide_depth = 0; ctx->info.bvh_wide_build_ms = 0;
     ctx->bvhDirty = false;
+    return BRT_OK;
+}
+// Width of the hierarchy the megakernel walks with the fast sampler: 2 = the binary LBVH itself, 4 / 8 = the wide collapse of it.
+// BRT_BVH_WIDTH (environment) overrides the render parameter — kernel A/B runs; 0 / unset = automatic.
+constexpr int WIDE_MAX_DEPTH = 32;                   // one shared-memory stack word per level and thread (16 KB / block at 32)
+static int wanted_width(const brt_ctx* ctx) {
+    int w = ctx->rp.bvh_width;
+    if (const char* e = getenv("BRT_BVH_WIDTH")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) w = v; }
+    if (w == 0) w = BRT_BVH_WIDTH_AUTO;
+    if (ctx->rp.sampler != BRT_SAMPLER_FAST || ctx->rp.integrator == BRT_INTEGRATOR_WAVEFRONT) return 2;
+    if (ctx->bin.nNodes >= (1LL << 24)) return 2;     // node ids share a stack word with the 8-bit pending mask
+    return w;
+}
+static int ensure_wide(brt_ctx* ctx) {
+    const int w = ctx->bvhDirty || ctx->dev.nNodes == 0 ? 2 : wanted_width(ctx);
+    if (w != 4 && w != 8) { ctx->dev.wnodes = nullptr; ctx->dev.wideN = 0; ctx->info.bvh_width = 2; return BRT_OK; }
+    if (ctx->wide.width != w) {
+        CK(build_wide(ctx->bin, w, &ctx->bvhWs, &ctx->wide, ctx->stream));
+        ctx->info.bvh_wide_depth = ctx->wide.depth; ctx->info.bvh_wide_build_ms = ctx->wide.buildMs;
+    }
+    if (!ctx->wide.wnodes || ctx->wide.depth > WIDE_MAX_DEPTH) {   // a degenerate chain of a tree: stay with the binary traversal (hybrid stack)
+        ctx->dev.wnodes = nullptr; ctx->dev.wideN = 0; ctx->info.bvh_width = 2;
+        return BRT_OK;
+    }
+    ctx->dev.wnodes = ctx->wide.wnodes; ctx->dev.wideN = w; ctx->dev.wideDepth = ctx->wide.depth; ctx->dev.wideAxes = ctx->wide.axes;
+    ctx->info.bvh_width = w;
     return BRT_OK;
 }
 // BRUTE reproduces the reference's loops; AUTO takes the hierarchy from 8 bounded primitives up (below that the linear loop wins)
@@ -387,6 +418,7 @@ int brt_scene_info_get(brt_ctx* ctx, brt_scene_info* out) {
     int rc = upload_scene(ctx);
     if (rc != BRT_OK) return rc;
     if ((rc = ensure_bvh(ctx)) != BRT_OK) return rc;               // the query reports the hierarchy, so it builds it
+    if ((rc = ensure_wide(ctx)) != BRT_OK) return rc;
     *out = ctx->info;
     return BRT_OK;
 }
@@ -441,6 +473,7 @@ int brt_set_render_params(brt_ctx* ctx, const brt_render_params* p) {
     if (p->aa_mode < 0 || p->aa_mode > 3 || p->tonemap < 0 || p->tonemap > 2) return fail(ctx, BRT_E_INVALID, "bad aa_mode / tonemap");
     if (p->sampler < 0 || p->sampler > 1 || p->integrator < 0 || p->integrator > 2 || p->accel < 0 || p->accel > 2)
         return fail(ctx, BRT_E_INVALID, "bad sampler / integrator / accel");
+    if (p->bvh_width != 0 && p->bvh_width != 2 && p->bvh_width != 4 && p->bvh_width != 8) return fail(ctx, BRT_E_INVALID, "bvh_width must be 0 (auto), 2, 4 or 8");
     ctx->rp = *p;
     return BRT_OK;
 }
@@ -477,6 +510,7 @@ int prepare(brt_ctx* ctx, PTParams& p) {
     int rc = upload_scene(ctx);
     if (rc != BRT_OK) return rc;
     if (wants_bvh(ctx) && (rc = ensure_bvh(ctx)) != BRT_OK) return rc;
+    if ((rc = ensure_wide(ctx)) != BRT_OK) return rc;
     if ((rc = upload_perm(ctx)) != BRT_OK) return rc;
     const brt_render_params& rp = ctx->rp;
     if (rp.sampler == BRT_SAMPLER_REFERENCE && (rc = ensure_prim64(ctx)) != BRT_OK) return rc;   // float64 primary-hit evaluation
@@ -499,6 +533,11 @@ int prepare(brt_ctx* ctx, PTParams& p) {
     }
     d32.lensRadius = (float)c.lens_radius; d32.type = c.type;
     p.W = rp.width; p.H = rp.height; p.maxDepth = rp.max_depth; p.aaMode = rp.aa_mode;
+    p.rowBegin = 0; p.rowEnd = rp.height;
+    if (const char* e = getenv("BRT_DEBUG_ROW_WINDOW")) {          // "a,b": trace rows [a, b) only (debug: brute force on a few rows of a big frame)
+        int a = 0, b = 0;
+        if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 0 && b > a) { p.rowBegin = a; p.rowEnd = b < rp.height ? b : rp.height; }
+    }
     p.seedLo = (uint32_t)rp.seed; p.seedHi = (uint32_t)(rp.seed >> 32);
     p.directLighting = rp.direct_lighting ? 1 : 0;
     p.refill = rp.refill_threshold > 0 ? (rp.refill_threshold > 32 ? 32 : rp.refill_threshold) : 8;
@@ -749,7 +788,7 @@ int brt_get_stats(brt_ctx* ctx, brt_stats* out) {
         ctx->stats.tests_tri_a = c[4]; ctx->stats.tests_tri_b = c[5]; ctx->stats.tests_tri_c = c[6]; ctx->stats.tests_aabb = c[7];
         ctx->stats.trav_warp_iters = c[8]; ctx->stats.trav_lane_iters = c[9]; ctx->stats.trav_alive_lanes = c[10];
         ctx->stats.trav_node_issues = c[11]; ctx->stats.trav_leaf_issues = c[12]; ctx->stats.trav_leaf_lanes = c[13];
-        ctx->stats.path_warp_iters = c[14]; ctx->stats.path_lane_iters = c[15];
+        ctx->stats.path_warp_iters = c[14]; ctx->stats.path_lane_iters = c[15]; ctx->stats.node_visits = c[16];
     }
     *out = ctx->stats;
     return BRT_OK;

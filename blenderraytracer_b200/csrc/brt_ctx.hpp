@@ -59,6 +59,8 @@ struct brt_ctx {
     DevBuf dArena, dPerm, dPrim64;
     PinnedBuf hStage;
     brt::BvhWorkspace bvhWs;
+    brt::BvhBuildResult bin{};                    // the binary hierarchy of the current scene
+    brt::WideBuildResult wide{};                  // its wide collapse (built when a launch wants it)
     brt::DevScene dev{};
     bool sceneDirty = true, permDirty = true, bvhDirty = true, prim64Dirty = true;
     int nBounded = 0;

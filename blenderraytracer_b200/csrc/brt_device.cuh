@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math_constants.h>
+#include <cstdio>
 
 namespace brt {
 
@@ -30,6 +31,8 @@ struct DevScene {
     const float4* mat;   // (r, g, b, param)                                 materials.js
     const int* matType;  // BRT_MAT_*
     const float4* nodes; // 4 x float4 per BVH node (see bvh.cu)
+    const float4* cnodes;// the same binary hierarchy with child boxes as centre / half-extent (bvh.cu: k_centre_half; node_visit_ch)
+    const float4* wnodes;// wide hierarchy collapsed from `nodes` (bvh.cu: k_wide_level): 2 x float4 per child slot, wideN slots per node
     const float4* lights;// 2 per light: (v.xyz, type), (color*intensity .xyz, 0)
     const unsigned char* perm;  // 512-entry doubled Perlin permutation      noise.js:7-17
     const float4* tex;    // 2 per texture: (odd.rgb, kind), (even.rgb, scale)        textures.js
@@ -42,6 +45,9 @@ struct DevScene {
     int bgKind;
     float bgR, bgG, bgB, skyIntensity;
     int bvhStackDepth;
+    int wideN;           // 0 = no wide hierarchy; 4 / 8 = children per wide node
+    int wideDepth;       // levels of the wide hierarchy (= traversal stack entries per ray)
+    int wideAxes;        // wideN == 4: the two axes (a0 | a1 << 2) whose ray signs order the four child slots
 };
 
 struct DevCamera {         // camera.js:14-35, derived on the host, kept in float64: primary rays are generated in double
@@ -71,6 +77,7 @@ struct Counters {          // counting build
     unsigned long long trLeafLanes;  // lanes that tested a leaf primitive
     unsigned long long mainIter;     // warp-level iterations of the path loop (one trace call each)
     unsigned long long mainLanes;    // lanes that executed them
+    unsigned long long nodeVisits;   // internal-node visits (binary: aabb / 2; wide: one per node, aabb counts its occupied slots)
 };
 constexpr int N_COUNTERS = sizeof(Counters) / sizeof(unsigned long long);
 
@@ -381,16 +388,47 @@ __device__ __forceinline__ bool node_visit(const float4* __restrict__ nodes, uin
     return h0 | h1;
 }
 
+// The same visit over the centre / half-extent copy of the node (fast-sampler megakernel):
+//   n0 = (c0.x, c0.y, c0.z, h0.x)  n1 = (h0.y, h0.z, c1.x, c1.y)  n2 = (c1.z, h1.x, h1.y, h1.z)  n3 = (child0, child1, -, -)
+//   [c - h, c + h] contains the lo / hi box; 56 of the 64 bytes are read (three 128-bit loads + one 64-bit), as for the lo / hi node
+// With tm = c*inv - ood the two slab planes of an axis are tm -+ h*|inv|: near and far are known WITHOUT the per-axis
+// min / max pair, so a child costs 9 FFMA + 2 FMNMX3 + 2 FMNMX instead of 6 FFMA + 6 FMNMX + 2 FMNMX3 + 2 FMNMX — 12 fewer
+// ALU-pipe instructions per visit for 6 more on the FMA pipe (the ALU pipe is the busiest pipe of this kernel, profiles/).
+// Same widening, same ordering rule; the boxes are supersets of the lo / hi boxes, so this can only add candidates.
+#ifndef BRT_NODE_CH
+#define BRT_NODE_CH 1
+#endif
+__device__ __forceinline__ bool node_visit_ch(const float4* __restrict__ nodes, uint32_t cur, const RayInv& r, float3 ainv, float tBest,
+                                              uint32_t& nearc, uint32_t& farc, bool& both) {
+    const float4* np = nodes + 4 * (size_t)cur;
+    const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
+    const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+    const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+    const float ax = fmaf(n0.x, r.inv.x, -r.ood.x), ay = fmaf(n0.y, r.inv.y, -r.ood.y), az = fmaf(n0.z, r.inv.z, -r.ood.z);
+    const float bx = fmaf(n1.z, r.inv.x, -r.ood.x), by = fmaf(n1.w, r.inv.y, -r.ood.y), bz = fmaf(n2.x, r.inv.z, -r.ood.z);
+    const float tn0 = fmaxf(fmax3(fmaf(-n0.w, ainv.x, ax), fmaf(-n1.x, ainv.y, ay), fmaf(-n1.y, ainv.z, az)), 0.f);
+    const float tf0 = fminf(fmin3(fmaf(n0.w, ainv.x, ax), fmaf(n1.x, ainv.y, ay), fmaf(n1.y, ainv.z, az)), tBest);
+    const float tn1 = fmaxf(fmax3(fmaf(-n2.y, ainv.x, bx), fmaf(-n2.z, ainv.y, by), fmaf(-n2.w, ainv.z, bz)), 0.f);
+    const float tf1 = fminf(fmin3(fmaf(n2.y, ainv.x, bx), fmaf(n2.z, ainv.y, by), fmaf(n2.w, ainv.z, bz)), tBest);
+    const bool h0 = tn0 <= __fmul_rn(tf0, 1.0000005f), h1 = tn1 <= __fmul_rn(tf1, 1.0000005f);
+    const bool swap = tn1 < tn0;
+    both = h0 & h1;
+    nearc = both ? (swap ? c1 : c0) : (h0 ? c0 : c1);
+    farc = swap ? c0 : c1;
+    return h0 | h1;
+}
+
 // Blocking traversal: runs one ray to completion.  HYBRID = false: the whole stack lives in shared memory (the launcher
 // sized it from the tree depth: depth + 1 entries per thread) and the loop carries no local-memory path at all;
 // HYBRID = true (trees deeper than SMEM_ONLY_MAX_DEPTH): SMEM_STACK entries in shared memory, the rest in a local array.
-template <bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY>
+template <bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY, bool CH = false>
 __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
                                          uint32_t* sstack /* &smem[threadIdx.x] */, int sstride, unsigned aliveMask = 0xffffffffu) {
     Hit best; best.t = tMax; best.pid = PID_NONE;
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
     if (sc.nNodes == 0) return best;
     RayInv r = ray_inv(O, D);
+    const float3 ainv = f3(fabsf(r.inv.x), fabsf(r.inv.y), fabsf(r.inv.z));
     int sp = 0;
     uint32_t cur = 0;
     uint32_t lstack[HYBRID ? LOCAL_STACK : 1];
@@ -411,9 +449,9 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
             test_prim<COUNT, SHADOW, PRIMS>(sc, cur & ~LEAF_BIT, O, D, tMin, self, best, cnt);
             if (SHADOW && best.pid != PID_NONE) break;
         } else {
-            if (COUNT) cnt.aabb += 2;
+            if (COUNT) { cnt.aabb += 2; cnt.nodeVisits++; }
             uint32_t nearc, farc; bool both;
-            if (node_visit(sc.nodes, cur, r, best.t, nearc, farc, both)) {
+            if (CH ? node_visit_ch(sc.cnodes, cur, r, ainv, best.t, nearc, farc, both) : node_visit(sc.nodes, cur, r, best.t, nearc, farc, both)) {
                 if (both) {
                     if (!HYBRID || sp < SMEM_STACK) sstack[sp * sstride] = farc; else lstack[sp - SMEM_STACK] = farc;
                     sp++;
@@ -425,6 +463,100 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
         if (sp == 0) break;
         sp--;
         cur = (!HYBRID || sp < SMEM_STACK) ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------- wide hierarchy
+// N-wide (4 or 8) hierarchy collapsed from the binary tree (bvh.cu: k_wide_level).  A wide node is N child slots of 32 bytes:
+//   A = (lo.x, hi.x, lo.y, hi.y)   B = (lo.z, hi.z, ref, -)      ref = LEAF_BIT | pid, or the id of the child's wide node;
+// empty slots hold lo.x = hi.x = +inf over finite y / z slabs and can never be hit.  The boxes are the binary tree's own (padded) boxes and the
+// slab arithmetic is node_visit's, so the wide traversal is exactly as conservative as the binary one: same hits, same images.
+// Order: the builder puts a child into the slot whose index bits say on which side of the node's centre it lies (bit a set = the
+// + side of axis a; N = 8: x, y, z; N = 4: the tree's two widest axes).  XOR-ing the slot index with the ray's direction-sign bits
+// gives a front-to-back visiting order (Ylitie et al. 2017), applied here to the ADDRESS of the slot loaded in step k, so hit-mask
+// bit k already is "k-th nearest slot" and the next child is simply the lowest set bit.  The stack holds one word per node that
+// still has pending children: node id << 8 | pending mask — one entry per LEVEL, not per far child.
+// Why wide at all on a GPU without RT cores: the dependent-load chain per ray shrinks from ~depth(binary) to ~depth / log2(N)
+// node visits (the 1 M-triangle terrain: 28 -> 10), the 2N slot loads of a visit are independent, a warp's rays need fewer
+// (longer) loop iterations, so the spread between the shortest and the longest traversal of a warp costs fewer idle slots.
+template <int N, bool COUNT, bool SHADOW, int PRIMS = PRIMS_ANY>
+__device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
+                                          uint32_t* sstack /* &smem[threadIdx.x] */, int sstride, unsigned aliveMask = 0xffffffffu) {
+    static_assert(N == 4 || N == 8, "wide hierarchy: 4 or 8 children per node");
+    Hit best; best.t = tMax; best.pid = PID_NONE;
+    test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
+    if (sc.nNodes == 0) return best;
+    const RayInv r = ray_inv(O, D);
+    uint32_t c;
+    if (N == 8) c = (D.x < 0.f ? 1u : 0u) | (D.y < 0.f ? 2u : 0u) | (D.z < 0.f ? 4u : 0u);
+    else {
+        const int a0 = sc.wideAxes & 3, a1 = (sc.wideAxes >> 2) & 3;
+        const float d0 = a0 == 0 ? D.x : a0 == 1 ? D.y : D.z, d1 = a1 == 0 ? D.x : a1 == 1 ? D.y : D.z;
+        c = (d0 < 0.f ? 1u : 0u) | (d1 < 0.f ? 2u : 0u);
+    }
+    const uint32_t c5 = c << 5;
+    const char* const base = reinterpret_cast<const char*>(sc.wnodes);
+    int sp = 0;
+    uint32_t g = 0u, node = 0u;
+    bool visit = true;
+    for (;;) {
+        if (COUNT && !SHADOW) {
+            const unsigned act = __activemask();
+            const unsigned nodeM = __ballot_sync(act, visit);
+            if ((int)(threadIdx.x & 31u) == __ffs(act) - 1) {
+                cnt.trIter++; cnt.trLanes += __popc(act); cnt.trAlive += __popc(aliveMask); cnt.trNodeIssue += nodeM ? 1 : 0;
+            }
+        }
+        if (visit) {
+#ifdef BRT_WIDE_DEBUG
+            if (node >= (uint32_t)sc.nNodes) { printf("wide: bad node %u (nNodes %d) sp %d g %08x\n", node, sc.nNodes, sp, g); __trap(); }
+#endif
+            const char* np = base + (size_t)node * (32u * N);
+            uint32_t m = 0u;
+            if (COUNT) cnt.nodeVisits++;
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                const float4* cp = reinterpret_cast<const float4*>(np + ((((uint32_t)k) << 5) ^ c5));
+                const float4 A = ldg4(cp), B = ldg4(cp + 1);
+                if (COUNT && A.x < CUDART_INF_F) cnt.aabb++;
+                const float x0 = fmaf(A.x, r.inv.x, -r.ood.x), x1 = fmaf(A.y, r.inv.x, -r.ood.x);
+                const float y0 = fmaf(A.z, r.inv.y, -r.ood.y), y1 = fmaf(A.w, r.inv.y, -r.ood.y);
+                const float z0 = fmaf(B.x, r.inv.z, -r.ood.z), z1 = fmaf(B.y, r.inv.z, -r.ood.z);
+                const float tn = fmaxf(fmax3(fminf(x0, x1), fminf(y0, y1), fminf(z0, z1)), 0.f);
+                const float tf = fminf(fmin3(fmaxf(x0, x1), fmaxf(y0, y1), fmaxf(z0, z1)), best.t);
+                if (tn <= __fmul_rn(tf, 1.0000005f)) m |= 1u << k;          // same widening as node_visit
+            }
+            g = (node << 8) | m;
+        }
+        if ((g & 0xFFu) == 0u) {
+            if (sp == 0) break;
+            sp--;
+            g = sstack[sp * sstride];
+        }
+        const uint32_t j = (uint32_t)__ffs((int)g) - 1u;                   // the nearest pending slot (traversal order)
+        g &= g - 1u;
+        const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(g >> 8) * (32u * N) + ((j << 5) ^ c5) + 24u));
+        const bool leaf = (ref & LEAF_BIT) != 0u;
+#ifdef BRT_WIDE_DEBUG
+        if (ref == 0xFFFFFFFFu || (!leaf && ref >= (uint32_t)sc.nNodes) || sp > sc.wideDepth - 1 || sp < 0) {
+            printf("wide: ref %08x j %u c %u g %08x sp %d depth %d\n", ref, j, c, g, sp, sc.wideDepth); __trap();
+        }
+#endif
+        if (COUNT && !SHADOW) {
+            const unsigned act = __activemask();
+            const unsigned leafM = __ballot_sync(act, leaf);
+            if ((int)(threadIdx.x & 31u) == __ffs(act) - 1) { cnt.trLeafIssue += leafM ? 1 : 0; cnt.trLeafLanes += __popc(leafM); }
+        }
+        if (leaf) {
+            test_prim<COUNT, SHADOW, PRIMS>(sc, ref & ~LEAF_BIT, O, D, tMin, self, best, cnt);
+            if (SHADOW && best.pid != PID_NONE) break;
+            visit = false;
+        } else {
+            if (g & 0xFFu) { sstack[sp * sstride] = g; sp++; }
+            node = ref;
+            visit = true;
+        }
     }
     return best;
 }

@@ -18,6 +18,7 @@ struct PTParams {
     DevCamera cam;
     DevCamera32 cam32;
     int W, H;
+    int rowBegin, rowEnd;        // only pixels of rows [rowBegin, rowEnd) are traced (the whole frame unless BRT_DEBUG_ROW_WINDOW narrows it: tools/rare_event_check.py)
     int sBegin, sCount;          // global sample indices [sBegin, sBegin + sCount) for every pixel
     int maxDepth;
     int aaMode;
@@ -94,14 +95,26 @@ cudaError_t launch_primary_aov64(const Obj64* objs, int nObjs, const double* mes
 struct BvhWorkspace {            // grow-only build memory, owned by the ctx (free_bvh_workspace at destroy)
     void* arena = nullptr; size_t arenaCap = 0;
     float4* nodes[2] = { nullptr, nullptr }; size_t nodeCap[2] = { 0, 0 };
+    float4* wide = nullptr; size_t wideCap = 0;         // wide hierarchy (build_wide)
+    int* level = nullptr; size_t levelCap = 0;
+    float4* cnodes = nullptr; size_t cnodeCap = 0;      // centre / half-extent copy of the chosen binary tree
 };
 void free_bvh_workspace(BvhWorkspace* ws);
 struct BvhBuildResult {
     float4* nodes;               // device, 4 x float4 per node, root = 0 (points into the workspace: do not free)
+    float4* cnodes;              // the same nodes with child boxes as centre / half-extent (node_visit_ch)
     long long nNodes;
     int depth;
     float buildMs;
+    float extent[3];             // extent of the primitive centroids' bounds per axis (the N = 4 wide collapse orders slots along the two widest)
 };
+struct WideBuildResult {
+    float4* wnodes = nullptr;    // device, 2 x float4 per child slot, `width` slots per node, node of binary node b at index b (root = 0)
+    int width = 0, depth = 0, axes = 0;
+    float buildMs = 0.f;
+};
+// collapses the binary hierarchy `bin` into a `width`-wide one (4 or 8); memory lives in the workspace
+cudaError_t build_wide(const BvhBuildResult& bin, int width, BvhWorkspace* ws, WideBuildResult* out, cudaStream_t st);
 // prim AABBs are computed on the device from the SoA arrays; pids = primitive ids of the bounded primitives
 cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out, cudaStream_t st);
 

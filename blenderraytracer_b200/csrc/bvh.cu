@@ -322,11 +322,188 @@ struct HostSah {
     }
 };
 
+// ---- centre / half-extent copy of the binary nodes (node_visit_ch) -------------------------------------------------------
+// c = (lo + hi) / 2 rounded to nearest, h = max(hi - c, c - lo) widened by 4 ulps: [c - h, c + h] contains [lo, hi] whatever
+// the rounding of the three operations, so the copy is at least as conservative as the original.
+__global__ void __launch_bounds__(256) k_centre_half(const float4* __restrict__ nodes, int nInternal, float4* __restrict__ cnodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nInternal) return;
+    const float4 n0 = nodes[4 * (size_t)i], n1 = nodes[4 * (size_t)i + 1], n2 = nodes[4 * (size_t)i + 2], n3 = nodes[4 * (size_t)i + 3];
+    const float lo[2][3] = { { n0.x, n0.z, n2.x }, { n1.x, n1.z, n2.z } }, hi[2][3] = { { n0.y, n0.w, n2.y }, { n1.y, n1.w, n2.w } };
+    float c[2][3], h[2][3];
+    for (int k = 0; k < 2; k++)
+        for (int a = 0; a < 3; a++) {
+            c[k][a] = 0.5f * lo[k][a] + 0.5f * hi[k][a];
+            h[k][a] = fmaxf(hi[k][a] - c[k][a], c[k][a] - lo[k][a]) * 1.0000005f + 1e-37f;
+        }
+    float4* cp = cnodes + 4 * (size_t)i;
+    cp[0] = make_float4(c[0][0], c[0][1], c[0][2], h[0][0]);
+    cp[1] = make_float4(h[0][1], h[0][2], c[1][0], c[1][1]);
+    cp[2] = make_float4(c[1][2], h[1][0], h[1][1], h[1][2]);
+    cp[3] = make_float4(n3.x, n3.y, 0.f, 0.f);
+}
+
+// ---- wide hierarchy: N-wide collapse of the binary tree --------------------------------------------------------------
+// One launch per level, top-down (launch L builds the wide nodes whose level is L and marks their internal children L + 1).
+// The wide node of binary node b lives at index b, so there is no allocation, no atomics and the result is deterministic;
+// only nodes reachable from the root are written.  Collapse rule: start from b's two children and keep replacing the internal
+// child with the largest surface area by its own two children until there are N children or only leaves are left (the
+// surface-area-guided collapse of Wald et al. 2008 / Ylitie et al. 2017).  Child boxes are copied from the binary nodes
+// unchanged.  Slot assignment: greedy maximisation of sum_i dot(centroid_i - centre, sign vector of slot_i) — see trace_wide.
+template <int N>
+__global__ void __launch_bounds__(128) k_wide_level(const float4* __restrict__ nodes, int nInternal, int level, int* __restrict__ levelOf,
+                                                    float4* __restrict__ wnodes, int axes, int* __restrict__ maxLevel) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nInternal) return;
+    if (level == 1 ? b != 0 : levelOf[b] != level) return;
+    uint32_t ref[N]; float lo[N][3], hi[N][3];
+    auto expand = [&](uint32_t id, int i0, int i1) {
+        const float4* np = nodes + 4 * (size_t)id;
+        const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+        lo[i0][0] = n0.x; hi[i0][0] = n0.y; lo[i0][1] = n0.z; hi[i0][1] = n0.w; lo[i0][2] = n2.x; hi[i0][2] = n2.y; ref[i0] = __float_as_uint(n3.x);
+        lo[i1][0] = n1.x; hi[i1][0] = n1.y; lo[i1][1] = n1.z; hi[i1][1] = n1.w; lo[i1][2] = n2.z; hi[i1][2] = n2.w; ref[i1] = __float_as_uint(n3.y);
+    };
+    expand((uint32_t)b, 0, 1);
+    int cnt = 2;
+    while (cnt < N) {
+        int pick = -1; float bestA = -1.f;
+        for (int i = 0; i < cnt; i++) {
+            if (ref[i] & LEAF_BIT) continue;
+            const float dx = hi[i][0] - lo[i][0], dy = hi[i][1] - lo[i][1], dz = hi[i][2] - lo[i][2];
+            const float a = dx * dy + dy * dz + dz * dx;
+            if (a > bestA) { bestA = a; pick = i; }
+        }
+        if (pick < 0) break;
+        expand(ref[pick], pick, cnt);
+        cnt++;
+    }
+    // slot assignment
+    float ctr[3];
+    for (int a = 0; a < 3; a++) {
+        float mn = lo[0][a], mx = hi[0][a];
+        for (int i = 1; i < cnt; i++) { mn = fminf(mn, lo[i][a]); mx = fmaxf(mx, hi[i][a]); }
+        ctr[a] = 0.5f * (mn + mx);
+    }
+    constexpr int NB = N == 8 ? 3 : 2;
+    int ax[3] = { 0, 1, 2 };
+    if (N == 4) { ax[0] = axes & 3; ax[1] = (axes >> 2) & 3; }
+    int slotOf[N], childAt[N];
+    for (int i = 0; i < N; i++) { slotOf[i] = -1; childAt[i] = -1; }
+    for (int round = 0; round < cnt; round++) {
+        int bi = -1, bs = -1; float bc = -CUDART_INF_F;
+        for (int i = 0; i < cnt; i++) {
+            if (slotOf[i] >= 0) continue;
+            for (int s2 = 0; s2 < N; s2++) {
+                if (childAt[s2] >= 0) continue;
+                float c = 0.f;
+                for (int k = 0; k < NB; k++) {
+                    const float d = 0.5f * (lo[i][ax[k]] + hi[i][ax[k]]) - ctr[ax[k]];
+                    c += ((s2 >> k) & 1) ? d : -d;
+                }
+                if (c > bc) { bc = c; bi = i; bs = s2; }
+            }
+        }
+        slotOf[bi] = bs; childAt[bs] = bi;
+    }
+    float4* wp = wnodes + (size_t)b * (2 * N);
+    bool anyInternal = false;
+    for (int s2 = 0; s2 < N; s2++) {
+        const int i = childAt[s2];
+        if (i < 0) {
+            // an empty slot: lo.x = hi.x = +inf, y and z slabs degenerate at 0.  Both x planes are then +inf (dir.x > 0: tn = +inf,
+            // while the finite y / z planes keep tf finite) or both -inf (dir.x < 0: tf = -inf), so the min / max slab test can
+            // never accept it, whatever the ray and even while the closest hit is still at +inf
+            wp[2 * s2] = make_float4(CUDART_INF_F, CUDART_INF_F, 0.f, 0.f);
+            wp[2 * s2 + 1] = make_float4(0.f, 0.f, __uint_as_float(0xFFFFFFFFu), 0.f);
+            continue;
+        }
+        wp[2 * s2] = make_float4(lo[i][0], hi[i][0], lo[i][1], hi[i][1]);
+        wp[2 * s2 + 1] = make_float4(lo[i][2], hi[i][2], __uint_as_float(ref[i]), 0.f);
+        if (!(ref[i] & LEAF_BIT)) { levelOf[ref[i]] = level + 1; anyInternal = true; }
+    }
+    if (anyInternal) atomicMax(maxLevel, level + 1);
+}
+
+cudaError_t build_wide(const BvhBuildResult& bin, int width, BvhWorkspace* ws, WideBuildResult* out, cudaStream_t st) {
+    *out = WideBuildResult{};
+    if (!bin.nodes || bin.nNodes < 1 || (width != 4 && width != 8)) return cudaSuccess;
+    const int nInternal = (int)bin.nNodes;
+    const size_t bytes = (size_t)nInternal * 32 * (size_t)width, lvlBytes = 4 * ((size_t)nInternal + 1);
+    cudaError_t e;
+    if (bytes > ws->wideCap) {
+        cudaFree(ws->wide); ws->wide = nullptr; ws->wideCap = 0;
+        if ((e = cudaMalloc(&ws->wide, bytes)) != cudaSuccess) return e;
+        ws->wideCap = bytes;
+    }
+    if (lvlBytes > ws->levelCap) {
+        cudaFree(ws->level); ws->level = nullptr; ws->levelCap = 0;
+        if ((e = cudaMalloc(&ws->level, lvlBytes)) != cudaSuccess) return e;
+        ws->levelCap = lvlBytes;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if ((e = cudaEventCreate(&e0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return e; }
+    cudaEventRecord(e0, st);
+    int* levelOf = ws->level;                         // [nInternal] level of every wide node (0 = not part of the wide tree), then maxLevel
+    int* maxLevel = levelOf + nInternal;
+    cudaMemsetAsync(levelOf, 0, lvlBytes, st);
+    // the N = 4 slot order uses the two axes along which the scene is widest
+    int axes = 0 | (2 << 2);
+    {
+        int order[3] = { 0, 1, 2 };
+        std::sort(order, order + 3, [&](int a, int b2) { return bin.extent[a] > bin.extent[b2] || (bin.extent[a] == bin.extent[b2] && a < b2); });
+        const int a0 = std::min(order[0], order[1]), a1 = std::max(order[0], order[1]);
+        axes = a0 | (a1 << 2);
+    }
+    const int blocks = (nInternal + 127) / 128;
+    // a wide level consumes at least one binary level, so `depth` launches reach every node (extra launches find nothing to do)
+    for (int level = 1; level <= bin.depth; level++) {
+        if (width == 8) k_wide_level<8><<<blocks, 128, 0, st>>>(bin.nodes, nInternal, level, levelOf, ws->wide, axes, maxLevel);
+        else k_wide_level<4><<<blocks, 128, 0, st>>>(bin.nodes, nInternal, level, levelOf, ws->wide, axes, maxLevel);
+    }
+    int maxL = 0;
+    cudaMemcpyAsync(&maxL, maxLevel, 4, cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(e1, st);
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) return e;
+    out->wnodes = ws->wide; out->width = width; out->depth = maxL < 1 ? 1 : maxL; out->axes = axes; out->buildMs = ms;
+    if (getenv("BRT_DEBUG")) {
+        // walk the wide tree on the host: structure check + shape statistics
+        std::vector<float4> h((size_t)nInternal * 2 * width);
+        std::vector<int> lv(nInternal);
+        cudaMemcpy(h.data(), ws->wide, bytes, cudaMemcpyDeviceToHost);
+        cudaMemcpy(lv.data(), levelOf, 4 * (size_t)nInternal, cudaMemcpyDeviceToHost);
+        long long nodesSeen = 0, kids = 0, leaves = 0, bad = 0; int deepest = 0;
+        std::vector<std::pair<uint32_t, int>> stack{ { 0u, 1 } };
+        while (!stack.empty()) {
+            auto [id, d] = stack.back(); stack.pop_back();
+            nodesSeen++; deepest = std::max(deepest, d);
+            if (id != 0 && lv[id] != d) bad++;
+            for (int s2 = 0; s2 < width; s2++) {
+                const float4 A = h[(size_t)id * 2 * width + 2 * s2], B = h[(size_t)id * 2 * width + 2 * s2 + 1];
+                if (!(A.x < FLT_MAX)) continue;
+                uint32_t r; memcpy(&r, &B.z, 4);
+                kids++;
+                if (r & LEAF_BIT) leaves++;
+                else if (r >= (uint32_t)nInternal) bad++;
+                else stack.push_back({ r, d + 1 });
+            }
+        }
+        fprintf(stderr, "[brt] wide-%d: %lld nodes (of %d binary), %.2f children / node, %lld leaves, depth %d (reported %d), %lld inconsistencies, %.3f ms\n",
+                width, nodesSeen, nInternal, nodesSeen ? (double)kids / nodesSeen : 0.0, leaves, deepest, out->depth, bad, ms);
+    }
+    return cudaSuccess;
+}
+
 #define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return e_; } } while (0)
 
 void free_bvh_workspace(BvhWorkspace* ws) {
     if (!ws) return;
-    cudaFree(ws->arena); cudaFree(ws->nodes[0]); cudaFree(ws->nodes[1]);
+    cudaFree(ws->arena); cudaFree(ws->nodes[0]); cudaFree(ws->nodes[1]); cudaFree(ws->wide); cudaFree(ws->level); cudaFree(ws->cnodes);
     *ws = BvhWorkspace{};
 }
 
@@ -334,7 +511,8 @@ void free_bvh_workspace(BvhWorkspace* ws) {
 // node buffers for the two candidate trees, so re-building for a new scene of similar size allocates nothing
 // (cudaMalloc / cudaFree of ~100 MB blocks cost far more than the 1 ms build itself).
 cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out, cudaStream_t st) {
-    out->nodes = nullptr; out->nNodes = 0; out->depth = 0; out->buildMs = 0.f;
+    out->nodes = nullptr; out->cnodes = nullptr; out->nNodes = 0; out->depth = 0; out->buildMs = 0.f;
+    out->extent[0] = out->extent[1] = out->extent[2] = 0.f;
     const int n = sc.nSph + sc.nBox + sc.nTri;
     if (n < 2) return cudaSuccess;                    // 0 or 1 bounded primitive: traversal falls back to the linear loop
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -378,6 +556,7 @@ cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out
     // two candidate hierarchies (Morton quantisation per axis / uniform); the one with the smaller surface-area cost is kept
     std::vector<double> hostSums(costBlocks);
     double bestCost = 0.0; int bestMode = -1, bestDepth = 0;
+    float hostSb[6] = { 0, 0, 0, 0, 0, 0 };
     for (int mode = 0; mode < 2; mode++) {
         float4* target = mode == 0 ? nodes : nodesAlt;
         k_morton<<<nb, 256, 0, st>>>(boxes, n, sb, mode, k0, v0);
@@ -395,6 +574,7 @@ cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out
         BVH_CK(cudaMemcpyAsync(hostSums.data(), blockSums, sizeof(double) * costBlocks, cudaMemcpyDeviceToHost, st));
         int depth = 0;
         BVH_CK(cudaMemcpyAsync(&depth, nodeDepth, 4, cudaMemcpyDeviceToHost, st));
+        if (mode == 0) BVH_CK(cudaMemcpyAsync(hostSb, sb, sizeof(hostSb), cudaMemcpyDeviceToHost, st));
         BVH_CK(cudaStreamSynchronize(st));
         double cost = 0.0;
         for (double v : hostSums) cost += v;
@@ -427,13 +607,20 @@ cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out
             nodes = target; bestCost = sah.cost; bestDepth = height; bestMode = 2;
         }
     }
+    if (nodeBytes > ws->cnodeCap) {
+        cudaFree(ws->cnodes); ws->cnodes = nullptr; ws->cnodeCap = 0;
+        BVH_CK(cudaMalloc(&ws->cnodes, nodeBytes));
+        ws->cnodeCap = nodeBytes;
+    }
+    k_centre_half<<<(n - 1 + 255) / 256, 256, 0, st>>>(nodes, n - 1, ws->cnodes);
     BVH_CK(cudaEventRecord(e1, st));
     BVH_CK(cudaGetLastError());
     BVH_CK(cudaEventSynchronize(e1));
     float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
     int depth = bestDepth;
     cleanup();
-    out->nodes = nodes; out->nNodes = n - 1; out->depth = depth; out->buildMs = ms;
+    out->nodes = nodes; out->cnodes = ws->cnodes; out->nNodes = n - 1; out->depth = depth; out->buildMs = ms;
+    for (int k = 0; k < 3; k++) out->extent[k] = hostSb[3 + k] - hostSb[k];
     return cudaSuccess;
 }
 

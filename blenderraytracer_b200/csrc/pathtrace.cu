@@ -18,13 +18,13 @@ namespace brt {
 // variant that dealt each tile's samples to the 32 lanes in balanced runs (lane L traces run r of pixel (L + r) mod 32,
 // order-independent fixed-point tile sums in shared memory) cut the drained share only to 6 % — what remains is the random
 // spread of 256-sample sums, not a systematic difference between pixels — and lost 2 % to its bookkeeping; it was removed.
-template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID, int PRIMS = PRIMS_ANY>
+template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID, int PRIMS = PRIMS_ANY, int WIDE = 0>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega(const __grid_constant__ PTParams p) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int row = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = col < p.W && row < p.H;
+    const bool inside = col < p.W && row < p.rowEnd && row >= p.rowBegin;
     const DevScene& sc = p.sc;
     // float64 primary rays + float64 evaluation of the primary hit: always with the sequential (reference) sampler — the mode
     // that is compared sample for sample with the float64 oracle — and in the AOV kernel; the fast sampler is fp32 throughout
@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
 #else
     constexpr bool PRECISE = SAMPLER == 1;
 #endif
+    constexpr bool CH = BRT_NODE_CH && SAMPLER == 0;                      // fast sampler: centre / half-extent node copy (node_visit_ch)
     Counters cnt = {};
     if (inside) {
         const int jUp = p.H - 1 - row;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 aliveMask = __activemask();
                 if (lane == __ffs(aliveMask) - 1) { cnt.mainIter++; cnt.mainLanes += __popc(aliveMask); }
             }
-            if (!(PRECISE && primaryDone)) h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
+            if (!(PRECISE && primaryDone)) h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS, WIDE, CH>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
             if (h.pid == PID_NONE) {                                          // ray-tracer.js:122
                 sum = sum + beta * background(sc, D);
                 continue;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                     } else { ldir = f3(-l0.x, -l0.y, -l0.z); ldist = CUDART_INF_F; }
                     float cosN = dot(sf.N, ldir);
                     if (!(cosN > 0.f)) continue;
-                    Hit sh = trace<USE_BVH, COUNT, true, HYBRID>(sc, sf.P, ldir, ldist, h.pid, cnt, sstack, PT_BLOCK);
+                    Hit sh = trace<USE_BVH, COUNT, true, HYBRID, PRIMS_ANY, WIDE, CH>(sc, sf.P, ldir, ldist, h.pid, cnt, sstack, PT_BLOCK);
                     if (sh.pid != PID_NONE) continue;
                     sum = sum + beta * (f3(m.x, m.y, m.z) * lcol) * cosN;
                 }
@@ -199,22 +200,38 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, float 
 }
 
 // ------------------------------------------------------------------------------------------- host launchers
+// the wide hierarchy: fast sampler only (the reference sampler decides primary visibility in float64 over the binary tree)
+template <int WIDE, bool COUNT, bool DIRECT>
+static cudaError_t launch_wide(const PTParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = (size_t)(p.sc.wideDepth < 1 ? 1 : p.sc.wideDepth) * PT_BLOCK * sizeof(uint32_t);   // one entry per level
+    if constexpr (!COUNT && !DIRECT) {
+        if (p.sc.nBox == 0 && p.sc.nTri == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_SPHERE, WIDE><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+        if (p.sc.nBox == 0 && p.sc.nSph == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_TRI, WIDE><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+    }
+    k_pathtrace_mega<0, true, COUNT, DIRECT, false, PRIMS_ANY, WIDE><<<grid, PT_BLOCK, smem, st>>>(p);
+    return cudaGetLastError();
+}
 template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT>
 static cudaError_t launch_pt3(const PTParams& p, dim3 grid, cudaStream_t st) {
-    if (!USE_BVH) {                                        // brute force: no traversal stack at all
+    if constexpr (!USE_BVH) {                              // brute force: no traversal stack at all
         k_pathtrace_mega<SAMPLER, false, COUNT, DIRECT, false><<<grid, PT_BLOCK, 0, st>>>(p);
         return cudaGetLastError();
+    } else {
+        if constexpr (SAMPLER == 0) {
+            if (p.sc.wideN == 8 && p.sc.wnodes) return launch_wide<8, COUNT, DIRECT>(p, grid, st);
+            if (p.sc.wideN == 4 && p.sc.wnodes) return launch_wide<4, COUNT, DIRECT>(p, grid, st);
+        }
+        // the stack: depth + 1 entries per thread, all in shared memory, unless the tree is unusually deep
+        const bool hybrid = p.sc.bvhStackDepth > SMEM_ONLY_MAX_DEPTH;
+        size_t smem = (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 1) * PT_BLOCK * sizeof(uint32_t);
+        if (hybrid) { k_pathtrace_mega<SAMPLER, true, COUNT, DIRECT, true><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+        if constexpr (SAMPLER == 0 && !COUNT && !DIRECT) {  // the common hot configurations get a leaf test without type dispatch
+            if (p.sc.nBox == 0 && p.sc.nTri == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_SPHERE><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+            if (p.sc.nBox == 0 && p.sc.nSph == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_TRI><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+        }
+        k_pathtrace_mega<SAMPLER, true, COUNT, DIRECT, false><<<grid, PT_BLOCK, smem, st>>>(p);
+        return cudaGetLastError();
     }
-    // the stack: depth + 1 entries per thread, all in shared memory, unless the tree is unusually deep
-    const bool hybrid = p.sc.bvhStackDepth > SMEM_ONLY_MAX_DEPTH;
-    size_t smem = (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 1) * PT_BLOCK * sizeof(uint32_t);
-    if (hybrid) k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, USE_BVH><<<grid, PT_BLOCK, smem, st>>>(p);
-    else if (SAMPLER == 0 && !COUNT && !DIRECT && p.sc.nBox == 0 && p.sc.nTri == 0)      // the common hot configurations get a
-        k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, false, PRIMS_SPHERE><<<grid, PT_BLOCK, smem, st>>>(p);   // leaf test
-    else if (SAMPLER == 0 && !COUNT && !DIRECT && p.sc.nBox == 0 && p.sc.nSph == 0)      // without type dispatch
-        k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, false, PRIMS_TRI><<<grid, PT_BLOCK, smem, st>>>(p);
-    else k_pathtrace_mega<SAMPLER, USE_BVH, COUNT, DIRECT, false><<<grid, PT_BLOCK, smem, st>>>(p);
-    return cudaGetLastError();
 }
 template <int SAMPLER, bool USE_BVH, bool COUNT>
 static cudaError_t launch_pt2(const PTParams& p, dim3 grid, cudaStream_t st) {

@@ -140,11 +140,15 @@ __device__ __forceinline__ bool scatter(const PTParams& p, int matWord, float4 m
     return scatter_drawn<SAMPLER>(p, matWord, m, sf, Din, r, rng, Dout, att);
 }
 
-template <bool USE_BVH, bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY>
+// WIDE = 0: the binary hierarchy (or the linear loops); 4 / 8: the wide hierarchy collapsed from it (megakernel, fast sampler)
+// CH: walk the centre / half-extent copy of the binary nodes (node_visit_ch) — the megakernel with the fast sampler
+template <bool USE_BVH, bool COUNT, bool SHADOW, bool HYBRID = true, int PRIMS = PRIMS_ANY, int WIDE = 0, bool CH = false>
 __device__ __forceinline__ Hit trace(const DevScene& sc, float3 O, float3 D, float tMax, uint32_t self, Counters& cnt,
                                      uint32_t* sstack, int sstride, unsigned aliveMask = 0xffffffffu) {
     if (COUNT && !SHADOW) cnt.rays++;
-    if (USE_BVH) return trace_bvh<COUNT, SHADOW, HYBRID, PRIMS>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride, aliveMask);
+    if (USE_BVH && WIDE == 8) return trace_wide<8, COUNT, SHADOW, PRIMS>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride, aliveMask);
+    if (USE_BVH && WIDE == 4) return trace_wide<4, COUNT, SHADOW, PRIMS>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride, aliveMask);
+    if (USE_BVH) return trace_bvh<COUNT, SHADOW, HYBRID, PRIMS, CH>(sc, O, D, 0.001f, tMax, self, cnt, sstack, sstride, aliveMask);
     return trace_brute<COUNT, SHADOW>(sc, O, D, 0.001f, tMax, self, cnt);
 }
 

@@ -371,6 +371,7 @@ class RayTracer:
         p.refill_threshold = int(getattr(self, "refillThreshold", 0))
         p.paths_in_flight = int(getattr(self, "pathsInFlight", 0))
         p.preview = 1 if getattr(self, "preview", False) else 0
+        p.bvh_width = int(getattr(self, "bvhWidth", 0))           # 0 = auto, 2 = binary LBVH, 4 / 8 = wide collapse (same images)
         L.check(self._ctx, self._L.brt_set_render_params(self._ctx, C.byref(p)))
         return p
 

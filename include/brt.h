@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BRT_ABI_VERSION 2
+#define BRT_ABI_VERSION 3
 
 typedef struct brt_ctx brt_ctx;
 
@@ -69,6 +69,7 @@ enum { BRT_SAMPLER_FAST = 0, BRT_SAMPLER_REFERENCE = 1 };
 enum { BRT_INTEGRATOR_AUTO = 0, BRT_INTEGRATOR_MEGAKERNEL = 1, BRT_INTEGRATOR_WAVEFRONT = 2 };
 /* BRUTE reproduces the reference's linear loops (world.js:24-30, geometry.js:253-259); BVH must give identical results. */
 enum { BRT_ACCEL_AUTO = 0, BRT_ACCEL_BRUTE = 1, BRT_ACCEL_BVH = 2 };
+#define BRT_BVH_WIDTH_AUTO 2   /* what bvh_width = 0 selects: the binary tree is the fastest on every measured config */
 
 /* ---- scene descriptors ----------------------------------------------------------------------------- */
 typedef struct brt_material {
@@ -154,7 +155,8 @@ typedef struct brt_render_params {
     int32_t paths_in_flight;     /* WAVEFRONT tuning: samples of a pixel in flight per lane (1..4); 0 = default (2) */
     int32_t preview;             /* 1 = progressive preview: before every progress callback the image of the samples traced so far
                                     is resolved into the caller's rgba8 buffer (the reference blits finished rows, ray-tracer.js:236-238) */
-    int32_t _pad1;
+    int32_t bvh_width;           /* children per hierarchy node walked by the megakernel with the FAST sampler: 0 = auto, 2 = the binary
+                                    LBVH, 4 / 8 = its wide collapse (results are identical; the reference has no hierarchy at all) */
 } brt_render_params;
 
 typedef struct brt_scene_info {
@@ -162,10 +164,13 @@ typedef struct brt_scene_info {
     int32_t n_spheres, n_planes, n_boxes;
     int64_t n_triangles;         /* standalone + mesh triangles */
     int64_t n_bvh_nodes;
-    int32_t bvh_depth, _pad;
+    int32_t bvh_depth;
+    int32_t bvh_width;           /* width of the hierarchy the current render parameters select: 2, 4 or 8 (0 = none built) */
     double bvh_build_ms;         /* device time of the LBVH build (Morton, radix sort, Karras, refit) */
     double upload_ms;
     int64_t upload_bytes;        /* host -> device bytes of the flattened SoA scene (primitives, meta, materials, lights) */
+    int32_t bvh_wide_depth, _pad;/* levels of the wide hierarchy (0 when the binary one is walked) */
+    double bvh_wide_build_ms;    /* device time of the wide collapse */
 } brt_scene_info;
 
 typedef struct brt_stats {
@@ -184,6 +189,7 @@ typedef struct brt_stats {
     uint64_t trav_warp_iters, trav_lane_iters, trav_alive_lanes;
     uint64_t trav_node_issues, trav_leaf_issues, trav_leaf_lanes;   /* warp iterations with >= 1 lane at a node / at a leaf; lanes at a leaf */
     uint64_t path_warp_iters, path_lane_iters;                       /* the path loop (one trace call per iteration) */
+    uint64_t node_visits;        /* internal-node visits (count_tests only); tests_aabb / node_visits = child boxes tested per visit */
 } brt_stats;
 
 typedef void (*brt_progress_cb)(double fraction, void* user);   /* onProgress (ray-tracer.js:258-259,279) */

@@ -193,7 +193,7 @@ static napi_value js_set_render_params(napi_env env, napi_callback_info info) {
     p.direct_lighting = get_i32(env, o, "directLighting", p.direct_lighting);
     p.sampler = get_i32(env, o, "sampler", p.sampler); p.accel = get_i32(env, o, "accel", p.accel);
     p.integrator = get_i32(env, o, "integrator", p.integrator); p.spp_batch = get_i32(env, o, "sppBatch", p.spp_batch);
-    p.preview = get_i32(env, o, "preview", p.preview);
+    p.preview = get_i32(env, o, "preview", p.preview); p.bvh_width = get_i32(env, o, "bvhWidth", p.bvh_width);
     int rc = brt_set_render_params(ctx, &p);
     if (rc != BRT_OK) return throw_brt(env, ctx, rc);
     napi_value u; napi_get_undefined(env, &u); return u;

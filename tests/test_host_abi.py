@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/brt.h but not exported by libbrt.so"
     assert set(syms) == set(L.SIGNATURES), set(syms) ^ set(L.SIGNATURES)       # the ctypes binding covers the header exactly
-    assert brt.load().brt_abi_version() == 2
+    assert brt.load().brt_abi_version() == 3
     assert b"sm_100a" in brt.load().brt_version()
 
 

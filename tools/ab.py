@@ -2,6 +2,7 @@
 `make -C blenderraytracer_b200/csrc B=build_x OUT=../libbrt_x.so EXTRA=-D...`, loaded through BRT_LIBBRT in its own process.
 
     python tools/ab.py base=blenderraytracer_b200/libbrt.so x=blenderraytracer_b200/libbrt_x.so -- c3:256 c5:64 c4:64
+    python tools/ab.py w2=blenderraytracer_b200/libbrt.so,BRT_BVH_WIDTH=2 w8=blenderraytracer_b200/libbrt.so,BRT_BVH_WIDTH=8 -- c3:256
 Prints best-of-5 kernel times (CUDA events around brt_render_accumulate) as Msamples/s, and the image checksum of each variant."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -31,8 +32,10 @@ for spec in sys.argv[1:]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); rt.renderAccumulate(acc.data_ptr(), 0, spp); e1.record(); torch.cuda.synchronize()
         if k: best = min(best, e0.elapsed_time(e1))
+    host = acc.cpu().numpy()
+    import zlib
     out[spec] = dict(ms=best, msamples_s=W * H * spp / best / 1e3, mean=float(acc[..., :3].mean().item() / spp),
-                     sha=hashlib.sha1(acc.cpu().numpy().tobytes()).hexdigest()[:12])
+                     sha=hashlib.sha1(host.tobytes()).hexdigest()[:12], rows=[zlib.crc32(host[y].tobytes()) for y in range(H)])
     rt.close()
 print("AB_RESULT " + json.dumps(out))
 ''' % ROOT
@@ -43,7 +46,9 @@ def main():
     variants, specs = [a.split("=", 1) for a in args[:cut]], args[cut + 1:]
     res = {}
     for name, lib in variants:
+        lib, *extra = lib.split(",")                      # name=path/to/lib.so[,ENV=VALUE ...]: environment of that variant's process
         env = dict(os.environ, BRT_LIBBRT=os.path.abspath(lib))
+        env.update(kv.split("=", 1) for kv in extra)
         p = subprocess.run([sys.executable, "-c", WORKER] + specs, capture_output=True, text=True, env=env, cwd=ROOT)
         line = [l for l in p.stdout.splitlines() if l.startswith("AB_RESULT ")]
         if not line:
@@ -56,9 +61,13 @@ def main():
         cells = []
         for s in specs:
             r, b = res[name][s], res[base][s]
-            cells.append(f"{r['msamples_s']:9.0f} {100 * (r['msamples_s'] / b['msamples_s'] - 1):+5.1f}% {'=' if r['sha'] == b['sha'] else '~'}{abs(r['mean'] - b['mean']):.0e}")
+            nrows = sum(1 for x, y in zip(r["rows"], b["rows"]) if x != y)   # image rows that differ from the base variant's
+            cells.append(f"{r['msamples_s']:9.0f} {100 * (r['msamples_s'] / b['msamples_s'] - 1):+5.1f}% {'=' if r['sha'] == b['sha'] else '~'}{nrows}r")
         print(f"{name:<14}" + "".join(f"{c:>26}" for c in cells))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    for v in res.values():
+        for r in v.values():
+            r.pop("rows", None)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "ab.json"), "w"), indent=1)
 
 if __name__ == "__main__":
