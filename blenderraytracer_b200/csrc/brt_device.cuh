@@ -388,13 +388,26 @@ __device__ __forceinline__ bool node_visit(const float4* __restrict__ nodes, uin
     return h0 | h1;
 }
 
-// The same visit over the centre / half-extent copy of the node (fast-sampler megakernel):
-//   n0 = (c0.x, c0.y, c0.z, h0.x)  n1 = (h0.y, h0.z, c1.x, c1.y)  n2 = (c1.z, h1.x, h1.y, h1.z)  n3 = (child0, child1, -, -)
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2: `fma.rn.f32x2`, `mul.rn.f32x2`): ONE instruction performs the IEEE operation on both
+// halves of a 64-bit register pair — same results as two scalar fmaf / __fmul_rn, half the issue slots.  ptxas folds a pair built
+// from one register into a broadcast operand (`R.F32`) and a negated pair into a negate modifier, so pk2(x, x) costs nothing.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+// The same visit over the centre / half-extent copy of the node (fast-sampler megakernel), children interleaved per axis:
+//   n0 = (c0.x, c1.x, c0.y, c1.y)  n1 = (c0.z, c1.z, h0.x, h1.x)  n2 = (h0.y, h1.y, h0.z, h1.z)  n3 = (child0, child1, -, -)
 //   [c - h, c + h] contains the lo / hi box; 56 of the 64 bytes are read (three 128-bit loads + one 64-bit), as for the lo / hi node
-// With tm = c*inv - ood the two slab planes of an axis are tm -+ h*|inv|: near and far are known WITHOUT the per-axis
-// min / max pair, so a child costs 9 FFMA + 2 FMNMX3 + 2 FMNMX instead of 6 FFMA + 6 FMNMX + 2 FMNMX3 + 2 FMNMX — 12 fewer
-// ALU-pipe instructions per visit for 6 more on the FMA pipe (the ALU pipe is the busiest pipe of this kernel, profiles/).
-// Same widening, same ordering rule; the boxes are supersets of the lo / hi boxes, so this can only add candidates.
+// With tm = c*inv - ood the two slab planes of an axis are tm -+ h*|inv|: near and far are known WITHOUT the per-axis min / max
+// pair, and each of the nine fused multiply-adds serves BOTH children (FFMA2 on the register pair a 128-bit load delivers).  A visit
+// is 9 FFMA2 + 4 FMNMX3 + 4 FMNMX + 1 FMUL2 where the lo / hi form needs 12 FFMA + 16 FMNMX + 4 FMNMX3 + 2 FMUL: 12 fewer
+// instructions on the ALU pipe (the busiest pipe of this kernel, profiles/) and 4 fewer on the FMA pipe.
+// Same widening, same ordering rule; the boxes are supersets of the lo / hi boxes.
 #ifndef BRT_NODE_CH
 #define BRT_NODE_CH 1
 #endif
@@ -404,13 +417,18 @@ __device__ __forceinline__ bool node_visit_ch(const float4* __restrict__ nodes, 
     const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
     const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
     const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
-    const float ax = fmaf(n0.x, r.inv.x, -r.ood.x), ay = fmaf(n0.y, r.inv.y, -r.ood.y), az = fmaf(n0.z, r.inv.z, -r.ood.z);
-    const float bx = fmaf(n1.z, r.inv.x, -r.ood.x), by = fmaf(n1.w, r.inv.y, -r.ood.y), bz = fmaf(n2.x, r.inv.z, -r.ood.z);
-    const float tn0 = fmaxf(fmax3(fmaf(-n0.w, ainv.x, ax), fmaf(-n1.x, ainv.y, ay), fmaf(-n1.y, ainv.z, az)), 0.f);
-    const float tf0 = fminf(fmin3(fmaf(n0.w, ainv.x, ax), fmaf(n1.x, ainv.y, ay), fmaf(n1.y, ainv.z, az)), tBest);
-    const float tn1 = fmaxf(fmax3(fmaf(-n2.y, ainv.x, bx), fmaf(-n2.z, ainv.y, by), fmaf(-n2.w, ainv.z, bz)), 0.f);
-    const float tf1 = fminf(fmin3(fmaf(n2.y, ainv.x, bx), fmaf(n2.z, ainv.y, by), fmaf(n2.w, ainv.z, bz)), tBest);
-    const bool h0 = tn0 <= __fmul_rn(tf0, 1.0000005f), h1 = tn1 <= __fmul_rn(tf1, 1.0000005f);
+    const unsigned long long tmx = fma2(pk2(n0.x, n0.y), pk2(r.inv.x, r.inv.x), pk2(-r.ood.x, -r.ood.x));
+    const unsigned long long tmy = fma2(pk2(n0.z, n0.w), pk2(r.inv.y, r.inv.y), pk2(-r.ood.y, -r.ood.y));
+    const unsigned long long tmz = fma2(pk2(n1.x, n1.y), pk2(r.inv.z, r.inv.z), pk2(-r.ood.z, -r.ood.z));
+    float nx0, nx1, ny0, ny1, nz0, nz1, fx0, fx1, fy0, fy1, fz0, fz1;
+    upk2(fma2(pk2(-n1.z, -n1.w), pk2(ainv.x, ainv.x), tmx), nx0, nx1); upk2(fma2(pk2(n1.z, n1.w), pk2(ainv.x, ainv.x), tmx), fx0, fx1);
+    upk2(fma2(pk2(-n2.x, -n2.y), pk2(ainv.y, ainv.y), tmy), ny0, ny1); upk2(fma2(pk2(n2.x, n2.y), pk2(ainv.y, ainv.y), tmy), fy0, fy1);
+    upk2(fma2(pk2(-n2.z, -n2.w), pk2(ainv.z, ainv.z), tmz), nz0, nz1); upk2(fma2(pk2(n2.z, n2.w), pk2(ainv.z, ainv.z), tmz), fz0, fz1);
+    const float tn0 = fmaxf(fmax3(nx0, ny0, nz0), 0.f), tn1 = fmaxf(fmax3(nx1, ny1, nz1), 0.f);
+    const float tf0 = fminf(fmin3(fx0, fy0, fz0), tBest), tf1 = fminf(fmin3(fx1, fy1, fz1), tBest);
+    float tw0, tw1;
+    upk2(mul2(pk2(tf0, tf1), pk2(1.0000005f, 1.0000005f)), tw0, tw1);
+    const bool h0 = tn0 <= tw0, h1 = tn1 <= tw1;
     const bool swap = tn1 < tn0;
     both = h0 & h1;
     nearc = both ? (swap ? c1 : c0) : (h0 ? c0 : c1);

@@ -337,9 +337,9 @@ __global__ void __launch_bounds__(256) k_centre_half(const float4* __restrict__ 
             h[k][a] = fmaxf(hi[k][a] - c[k][a], c[k][a] - lo[k][a]) * 1.0000005f + 1e-37f;
         }
     float4* cp = cnodes + 4 * (size_t)i;
-    cp[0] = make_float4(c[0][0], c[0][1], c[0][2], h[0][0]);
-    cp[1] = make_float4(h[0][1], h[0][2], c[1][0], c[1][1]);
-    cp[2] = make_float4(c[1][2], h[1][0], h[1][1], h[1][2]);
+    cp[0] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);          // children interleaved per axis: one 64-bit register
+    cp[1] = make_float4(c[0][2], c[1][2], h[0][0], h[1][0]);          // pair = the same quantity of both children (FFMA2)
+    cp[2] = make_float4(h[0][1], h[1][1], h[0][2], h[1][2]);
     cp[3] = make_float4(n3.x, n3.y, 0.f, 0.f);
 }
 
