@@ -427,7 +427,7 @@ def measure(env: Env, args, name: str, spp_total: int, steps: int, warmup: int, 
                     "rays_per_sample": st["rays"] / max(1, W * H * my_count),
                     # quantities that only move the right way when the kernel or the hierarchy gets better (a worse tree inflates `achieved`)
                     "grays_per_s": st["rays"] / (kern_ms_avg * 1e-3) / 1e9,
-                    "slab_tests_per_ray": st["tests_aabb"] / rays, "node_visits_per_ray": st["tests_aabb"] / 2 / rays,
+                    "slab_tests_per_ray": st["tests_aabb"] / rays, "node_visits_per_ray": st["node_visits"] / rays,
                     "prim_tests_per_ray": (st["tests_sphere"] + st["tests_box"] + st["tests_tri_a"] + st["tests_plane"]) / rays,
                     "lane_slots": {"working": st["trav_lane_iters"] / slots, "waiting_for_slowest_ray": (st["trav_alive_lanes"] - st["trav_lane_iters"]) / slots,
                                    "drained": (slots - st["trav_alive_lanes"]) / slots,
@@ -466,7 +466,7 @@ def measure(env: Env, args, name: str, spp_total: int, steps: int, warmup: int, 
             "run": {"spp_per_gpu": my_count, "sampler": args.sampler, "accel": "bvh" if info["n_bvh_nodes"] and args.accel != "brute" else "brute",
                     "integrator": integ, "exchange": (sr.reduce if sr else "none"),
                     "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks",
-                    "bvh_nodes": info["n_bvh_nodes"], "bvh_depth": info["bvh_depth"], "bvh_build_ms": info["bvh_build_ms"],
+                    "bvh_nodes": info["n_bvh_nodes"], "bvh_depth": info["bvh_depth"], "bvh_width": info["bvh_width"], "bvh_build_ms": info["bvh_build_ms"],
                     "scene_ingest_s": ingest_s, "scene_upload_ms": info["upload_ms"]},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(W * H * 4),

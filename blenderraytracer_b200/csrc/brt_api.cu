@@ -347,7 +347,7 @@ static int ensure_bvh(brt_ctx* ctx) {
     if (!ctx->bvhDirty) return BRT_OK;
     BvhBuildResult br{};
     CK(build_lbvh(ctx->dev, &ctx->bvhWs, &br, ctx->stream));
-    if (br.depth > SMEM_STACK + LOCAL_STACK) return fail(ctx, BRT_E_STATE, "LBVH deeper than the traversal stack (" + std::to_string(br.depth) + ")");
+    if (br.depth + 1 > SMEM_STACK + LOCAL_STACK) return fail(ctx, BRT_E_STATE, "LBVH deeper than the traversal stack (" + std::to_string(br.depth) + ")");
     ctx->dev.nodes = br.nodes; ctx->dev.cnodes = br.cnodes; ctx->dev.nNodes = (int)br.nNodes; ctx->dev.bvhStackDepth = br.depth;
     ctx->info.n_bvh_nodes = br.nNodes; ctx->info.bvh_depth = br.depth; ctx->info.bvh_build_ms = br.buildMs;
     ctx->bin = br; ctx->wide = WideBuildResult{};

@@ -344,6 +344,8 @@ constexpr int LOCAL_STACK = 52;
 constexpr int SMEM_ONLY_MAX_DEPTH = 32;   // trees up to this depth run with the whole stack in shared memory (16.5 KB / block at 32)
 constexpr uint32_t TRAV_DONE = 0xFFFFFFFFu;
 
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 struct RayInv { float3 inv, ood; };
 // A direction component that is exactly 0 (axis-parallel camera rays through the centre row / column, mirror bounces off
 // axis-aligned faces) or denormal would make inv = +-inf and `bound*inv - ood` = inf - inf = NaN on a slab that straddles the
@@ -411,11 +413,22 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
 #ifndef BRT_NODE_CH
 #define BRT_NODE_CH 1
 #endif
+#ifndef BRT_NODE_LDG256
+#define BRT_NODE_LDG256 0      // two LDG.E.256 per node instead of 3 x 128 + 64 bit: measured C5 -1.3 %, C3 / C4 +0.4 %, C2 +1.1 % (B200) — off
+#endif
 __device__ __forceinline__ bool node_visit_ch(const float4* __restrict__ nodes, uint32_t cur, const RayInv& r, float3 ainv, float tBest,
                                               uint32_t& nearc, uint32_t& farc, bool& both) {
     const float4* np = nodes + 4 * (size_t)cur;
+#if BRT_NODE_LDG256
+    // the 64-byte node in TWO 256-bit read-only loads (sm_100 LDG.E.256) instead of three 128-bit + one 64-bit: half the
+    // load instructions and half the L1 requests of a visit whose lanes all sit at different nodes
+    float4 n0, n1, n2; float2 n3; float pad0, pad1;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(pad0), "=f"(pad1) : "l"(np + 2));
+#else
     const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
     const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+#endif
     const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
     const unsigned long long tmx = fma2(pk2(n0.x, n0.y), pk2(r.inv.x, r.inv.x), pk2(-r.ood.x, -r.ood.x));
     const unsigned long long tmy = fma2(pk2(n0.z, n0.w), pk2(r.inv.y, r.inv.y), pk2(-r.ood.y, -r.ood.y));
@@ -447,13 +460,21 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
     if (sc.nNodes == 0) return best;
     RayInv r = ray_inv(O, D);
     const float3 ainv = f3(fabsf(r.inv.x), fabsf(r.inv.y), fabsf(r.inv.z));
-    int sp = 0;
-    uint32_t cur = 0;
     uint32_t lstack[HYBRID ? LOCAL_STACK : 1];
     // (A variant with a uniform tail — far child stored unconditionally, "pop" as a select on a stack top that every lane
     // loads each iteration — removed the divergent pop block, 6-8 % of issued instructions at 6-7 lanes, but put a shared-memory
     // load on every iteration's critical path: C3 -2.8 %, C5 -0.9 %, C4 +3.3 % on a B200.  The branchy form stays.)
-    for (;;) {
+    // The bottom stack entry is a sentinel: popping it ends the loop, so a pop needs no emptiness test and the loop has ONE
+    // back edge and one exit (the multi-exit form made ptxas copy best.t / best.pid between two register sets every iteration).
+    // shared-memory stack through its 32-bit shared address, kept opaque so that ptxas holds it in a register instead of
+    // re-deriving it from %tid at every push / pop (S2R + 4 instructions when it rematerialises)
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sstack);
+    asm volatile("" : "+r"(sbase));
+    const uint32_t sstep = (uint32_t)sstride * 4u;
+    sts32(sbase, TRAV_DONE);
+    int sp = 1;
+    uint32_t cur = 0;
+    do {
         if (COUNT && !SHADOW) {
             // lane attribution: which lanes of the warp execute this iteration, and doing what (profiles/*lane_attribution*)
             const unsigned act = __activemask();
@@ -463,6 +484,7 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
                 cnt.trLeafIssue += leafM ? 1 : 0; cnt.trNodeIssue += (leafM != act) ? 1 : 0; cnt.trLeafLanes += __popc(leafM);
             }
         }
+        bool pop = true;
         if (cur & LEAF_BIT) {
             test_prim<COUNT, SHADOW, PRIMS>(sc, cur & ~LEAF_BIT, O, D, tMin, self, best, cnt);
             if (SHADOW && best.pid != PID_NONE) break;
@@ -471,17 +493,18 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
             uint32_t nearc, farc; bool both;
             if (CH ? node_visit_ch(sc.cnodes, cur, r, ainv, best.t, nearc, farc, both) : node_visit(sc.nodes, cur, r, best.t, nearc, farc, both)) {
                 if (both) {
-                    if (!HYBRID || sp < SMEM_STACK) sstack[sp * sstride] = farc; else lstack[sp - SMEM_STACK] = farc;
+                    if (!HYBRID || sp < SMEM_STACK) sts32(sbase + (uint32_t)sp * sstep, farc); else lstack[sp - SMEM_STACK] = farc;
                     sp++;
                 }
                 cur = nearc;
-                continue;
+                pop = false;
             }
         }
-        if (sp == 0) break;
-        sp--;
-        cur = (!HYBRID || sp < SMEM_STACK) ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
-    }
+        if (pop) {
+            sp--;
+            cur = (!HYBRID || sp < SMEM_STACK) ? lds32(sbase + (uint32_t)sp * sstep) : lstack[sp - SMEM_STACK];
+        }
+    } while (cur != TRAV_DONE);
     return best;
 }
 

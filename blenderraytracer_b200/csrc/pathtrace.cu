@@ -223,7 +223,7 @@ static cudaError_t launch_pt3(const PTParams& p, dim3 grid, cudaStream_t st) {
         }
         // the stack: depth + 1 entries per thread, all in shared memory, unless the tree is unusually deep
         const bool hybrid = p.sc.bvhStackDepth > SMEM_ONLY_MAX_DEPTH;
-        size_t smem = (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 1) * PT_BLOCK * sizeof(uint32_t);
+        size_t smem = (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 2) * PT_BLOCK * sizeof(uint32_t);   // + the sentinel entry
         if (hybrid) { k_pathtrace_mega<SAMPLER, true, COUNT, DIRECT, true><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
         if constexpr (SAMPLER == 0 && !COUNT && !DIRECT) {  // the common hot configurations get a leaf test without type dispatch
             if (p.sc.nBox == 0 && p.sc.nTri == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_SPHERE><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
