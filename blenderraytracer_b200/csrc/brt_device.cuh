@@ -416,6 +416,23 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
 #ifndef BRT_NODE_LDG256
 #define BRT_NODE_LDG256 0      // two LDG.E.256 per node instead of 3 x 128 + 64 bit: measured C5 -1.3 %, C3 / C4 +0.4 %, C2 +1.1 % (B200) — off
 #endif
+// Slab test of the TWO boxes of one 64-byte centre / half-extent record (see node_visit_ch for the layout): 9 FFMA2 + 1 FMUL2.
+// -> entry distances tn and widened exit distances tw of both boxes; box k is hit iff tn_k <= tw_k (the comparisons are left to
+// the caller: handed back as bool references they are materialised as 0 / 1 integers instead of predicates)
+__device__ __forceinline__ void pair_slabs(float4 n0, float4 n1, float4 n2, const RayInv& r, float3 ainv, float tBest,
+                                           float& tn0, float& tn1, float& tw0, float& tw1) {
+    const unsigned long long tmx = fma2(pk2(n0.x, n0.y), pk2(r.inv.x, r.inv.x), pk2(-r.ood.x, -r.ood.x));
+    const unsigned long long tmy = fma2(pk2(n0.z, n0.w), pk2(r.inv.y, r.inv.y), pk2(-r.ood.y, -r.ood.y));
+    const unsigned long long tmz = fma2(pk2(n1.x, n1.y), pk2(r.inv.z, r.inv.z), pk2(-r.ood.z, -r.ood.z));
+    float nx0, nx1, ny0, ny1, nz0, nz1, fx0, fx1, fy0, fy1, fz0, fz1;
+    upk2(fma2(pk2(-n1.z, -n1.w), pk2(ainv.x, ainv.x), tmx), nx0, nx1); upk2(fma2(pk2(n1.z, n1.w), pk2(ainv.x, ainv.x), tmx), fx0, fx1);
+    upk2(fma2(pk2(-n2.x, -n2.y), pk2(ainv.y, ainv.y), tmy), ny0, ny1); upk2(fma2(pk2(n2.x, n2.y), pk2(ainv.y, ainv.y), tmy), fy0, fy1);
+    upk2(fma2(pk2(-n2.z, -n2.w), pk2(ainv.z, ainv.z), tmz), nz0, nz1); upk2(fma2(pk2(n2.z, n2.w), pk2(ainv.z, ainv.z), tmz), fz0, fz1);
+    tn0 = fmaxf(fmax3(nx0, ny0, nz0), 0.f); tn1 = fmaxf(fmax3(nx1, ny1, nz1), 0.f);
+    const float tf0 = fminf(fmin3(fx0, fy0, fz0), tBest), tf1 = fminf(fmin3(fx1, fy1, fz1), tBest);
+    // conservative: boxes are inflated at build time and the far bound is widened by a few ulps (see node_visit)
+    upk2(mul2(pk2(tf0, tf1), pk2(1.0000005f, 1.0000005f)), tw0, tw1);
+}
 __device__ __forceinline__ bool node_visit_ch(const float4* __restrict__ nodes, uint32_t cur, const RayInv& r, float3 ainv, float tBest,
                                               uint32_t& nearc, uint32_t& farc, bool& both) {
     const float4* np = nodes + 4 * (size_t)cur;
@@ -430,17 +447,8 @@ __device__ __forceinline__ bool node_visit_ch(const float4* __restrict__ nodes, 
     const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
 #endif
     const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
-    const unsigned long long tmx = fma2(pk2(n0.x, n0.y), pk2(r.inv.x, r.inv.x), pk2(-r.ood.x, -r.ood.x));
-    const unsigned long long tmy = fma2(pk2(n0.z, n0.w), pk2(r.inv.y, r.inv.y), pk2(-r.ood.y, -r.ood.y));
-    const unsigned long long tmz = fma2(pk2(n1.x, n1.y), pk2(r.inv.z, r.inv.z), pk2(-r.ood.z, -r.ood.z));
-    float nx0, nx1, ny0, ny1, nz0, nz1, fx0, fx1, fy0, fy1, fz0, fz1;
-    upk2(fma2(pk2(-n1.z, -n1.w), pk2(ainv.x, ainv.x), tmx), nx0, nx1); upk2(fma2(pk2(n1.z, n1.w), pk2(ainv.x, ainv.x), tmx), fx0, fx1);
-    upk2(fma2(pk2(-n2.x, -n2.y), pk2(ainv.y, ainv.y), tmy), ny0, ny1); upk2(fma2(pk2(n2.x, n2.y), pk2(ainv.y, ainv.y), tmy), fy0, fy1);
-    upk2(fma2(pk2(-n2.z, -n2.w), pk2(ainv.z, ainv.z), tmz), nz0, nz1); upk2(fma2(pk2(n2.z, n2.w), pk2(ainv.z, ainv.z), tmz), fz0, fz1);
-    const float tn0 = fmaxf(fmax3(nx0, ny0, nz0), 0.f), tn1 = fmaxf(fmax3(nx1, ny1, nz1), 0.f);
-    const float tf0 = fminf(fmin3(fx0, fy0, fz0), tBest), tf1 = fminf(fmin3(fx1, fy1, fz1), tBest);
-    float tw0, tw1;
-    upk2(mul2(pk2(tf0, tf1), pk2(1.0000005f, 1.0000005f)), tw0, tw1);
+    float tn0, tn1, tw0, tw1;
+    pair_slabs(n0, n1, n2, r, ainv, tBest, tn0, tn1, tw0, tw1);
     const bool h0 = tn0 <= tw0, h1 = tn1 <= tw1;
     const bool swap = tn1 < tn0;
     both = h0 & h1;
@@ -509,18 +517,23 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
 }
 
 // ------------------------------------------------------------------------------------------- wide hierarchy
-// N-wide (4 or 8) hierarchy collapsed from the binary tree (bvh.cu: k_wide_level).  A wide node is N child slots of 32 bytes:
-//   A = (lo.x, hi.x, lo.y, hi.y)   B = (lo.z, hi.z, ref, -)      ref = LEAF_BIT | pid, or the id of the child's wide node;
-// empty slots hold lo.x = hi.x = +inf over finite y / z slabs and can never be hit.  The boxes are the binary tree's own (padded) boxes and the
-// slab arithmetic is node_visit's, so the wide traversal is exactly as conservative as the binary one: same hits, same images.
+// N-wide (4 or 8) hierarchy collapsed from the binary tree (bvh.cu: k_wide_level).  A wide node is N / 2 PAIR RECORDS of 64 bytes,
+// each holding two child slots in exactly the layout of a centre / half-extent binary node (node_visit_ch):
+//   (cA.x, cB.x, cA.y, cB.y) (cA.z, cB.z, hA.x, hB.x) (hA.y, hB.y, hA.z, hB.z) (refA, refB, -, -)
+// ref = LEAF_BIT | pid, or the id of the child's wide node; an empty slot has h.x = -inf (near = +inf, far = -inf: never hit).
+// The boxes contain the binary tree's (padded) boxes and the slab arithmetic is pair_slabs — the same nine FFMA2 per TWO children
+// as the binary visit — so the wide traversal is as conservative as the binary one: same hits, same images.
 // Order: the builder puts a child into the slot whose index bits say on which side of the node's centre it lies (bit a set = the
 // + side of axis a; N = 8: x, y, z; N = 4: the tree's two widest axes).  XOR-ing the slot index with the ray's direction-sign bits
-// gives a front-to-back visiting order (Ylitie et al. 2017), applied here to the ADDRESS of the slot loaded in step k, so hit-mask
-// bit k already is "k-th nearest slot" and the next child is simply the lowest set bit.  The stack holds one word per node that
-// still has pending children: node id << 8 | pending mask — one entry per LEVEL, not per far child.
-// Why wide at all on a GPU without RT cores: the dependent-load chain per ray shrinks from ~depth(binary) to ~depth / log2(N)
-// node visits (the 1 M-triangle terrain: 28 -> 10), the 2N slot loads of a visit are independent, a warp's rays need fewer
-// (longer) loop iterations, so the spread between the shortest and the longest traversal of a warp costs fewer idle slots.
+// gives a front-to-back visiting order (Ylitie et al. 2017): the upper bits of that XOR are applied to the ADDRESS of the pair record
+// loaded in step k, the lowest bit by swapping adjacent bits of the hit mask, so mask bit j is "j-th nearest slot" and the next
+// child is simply the lowest set bit.  The stack holds one word per node that still has pending children (node id << 8 | pending
+// mask) — one entry per LEVEL, not per far child.
+// Measured on a B200 (profiles/r02_wide_hierarchy.md): the wide trees test the SAME number of boxes per ray as the binary tree at
+// N = 4 (C5 55.4 vs 55.7, C3 19.6 vs 18.8) in half the node visits (C5 14.2 vs 27.9, N = 8: 9.8), but a visit costs more than
+// N / 2 binary visits here — mask assembly, the pending-slot pick with its dependent ref load, the pair addressing — so the
+// binary walk stays faster on every config but the Cornell box (N = 4: C3 -13 %, C5 -4 %; N = 8: C3 -25 %, C5 -23 %, C4 +0.3 %).
+// bvh_width = 0 (auto) therefore selects the binary tree; 4 / 8 stay selectable, with identical images.
 template <int N, bool COUNT, bool SHADOW, int PRIMS = PRIMS_ANY>
 __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
                                           uint32_t* sstack /* &smem[threadIdx.x] */, int sstride, unsigned aliveMask = 0xffffffffu) {
@@ -529,6 +542,7 @@ __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
     if (sc.nNodes == 0) return best;
     const RayInv r = ray_inv(O, D);
+    const float3 ainv = f3(fabsf(r.inv.x), fabsf(r.inv.y), fabsf(r.inv.z));
     uint32_t c;
     if (N == 8) c = (D.x < 0.f ? 1u : 0u) | (D.y < 0.f ? 2u : 0u) | (D.z < 0.f ? 4u : 0u);
     else {
@@ -536,8 +550,11 @@ __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D
         const float d0 = a0 == 0 ? D.x : a0 == 1 ? D.y : D.z, d1 = a1 == 0 ? D.x : a1 == 1 ? D.y : D.z;
         c = (d0 < 0.f ? 1u : 0u) | (d1 < 0.f ? 2u : 0u);
     }
-    const uint32_t c5 = c << 5;
+    const uint32_t cp6 = (c >> 1) << 6;                // pair-record address XOR
     const char* const base = reinterpret_cast<const char*>(sc.wnodes);
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sstack);
+    asm volatile("" : "+r"(sbase));
+    const uint32_t sstep = (uint32_t)sstride * 4u;
     int sp = 0;
     uint32_t g = 0u, node = 0u;
     bool visit = true;
@@ -550,40 +567,31 @@ __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D
             }
         }
         if (visit) {
-#ifdef BRT_WIDE_DEBUG
-            if (node >= (uint32_t)sc.nNodes) { printf("wide: bad node %u (nNodes %d) sp %d g %08x\n", node, sc.nNodes, sp, g); __trap(); }
-#endif
             const char* np = base + (size_t)node * (32u * N);
             uint32_t m = 0u;
             if (COUNT) cnt.nodeVisits++;
 #pragma unroll
-            for (int k = 0; k < N; k++) {
-                const float4* cp = reinterpret_cast<const float4*>(np + ((((uint32_t)k) << 5) ^ c5));
-                const float4 A = ldg4(cp), B = ldg4(cp + 1);
-                if (COUNT && A.x < CUDART_INF_F) cnt.aabb++;
-                const float x0 = fmaf(A.x, r.inv.x, -r.ood.x), x1 = fmaf(A.y, r.inv.x, -r.ood.x);
-                const float y0 = fmaf(A.z, r.inv.y, -r.ood.y), y1 = fmaf(A.w, r.inv.y, -r.ood.y);
-                const float z0 = fmaf(B.x, r.inv.z, -r.ood.z), z1 = fmaf(B.y, r.inv.z, -r.ood.z);
-                const float tn = fmaxf(fmax3(fminf(x0, x1), fminf(y0, y1), fminf(z0, z1)), 0.f);
-                const float tf = fminf(fmin3(fmaxf(x0, x1), fmaxf(y0, y1), fmaxf(z0, z1)), best.t);
-                if (tn <= __fmul_rn(tf, 1.0000005f)) m |= 1u << k;          // same widening as node_visit
+            for (int k = 0; k < N / 2; k++) {
+                const float4* pp = reinterpret_cast<const float4*>(np + ((((uint32_t)k) << 6) ^ cp6));
+                const float4 n0 = ldg4(pp), n1 = ldg4(pp + 1), n2 = ldg4(pp + 2);
+                if (COUNT) cnt.aabb += (n1.z >= 0.f ? 1 : 0) + (n1.w >= 0.f ? 1 : 0);      // occupied slots
+                float tn0, tn1, tw0, tw1;
+                pair_slabs(n0, n1, n2, r, ainv, best.t, tn0, tn1, tw0, tw1);
+                if (tn0 <= tw0) m |= 1u << (2 * k);
+                if (tn1 <= tw1) m |= 2u << (2 * k);
             }
+            if (c & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
             g = (node << 8) | m;
         }
         if ((g & 0xFFu) == 0u) {
             if (sp == 0) break;
             sp--;
-            g = sstack[sp * sstride];
+            g = lds32(sbase + (uint32_t)sp * sstep);
         }
-        const uint32_t j = (uint32_t)__ffs((int)g) - 1u;                   // the nearest pending slot (traversal order)
+        const uint32_t slot = ((uint32_t)__ffs((int)g) - 1u) ^ c;          // the nearest pending slot (traversal order -> slot)
         g &= g - 1u;
-        const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(g >> 8) * (32u * N) + ((j << 5) ^ c5) + 24u));
+        const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(g >> 8) * (32u * N) + ((slot >> 1) << 6) + 48u + ((slot & 1u) << 2)));
         const bool leaf = (ref & LEAF_BIT) != 0u;
-#ifdef BRT_WIDE_DEBUG
-        if (ref == 0xFFFFFFFFu || (!leaf && ref >= (uint32_t)sc.nNodes) || sp > sc.wideDepth - 1 || sp < 0) {
-            printf("wide: ref %08x j %u c %u g %08x sp %d depth %d\n", ref, j, c, g, sp, sc.wideDepth); __trap();
-        }
-#endif
         if (COUNT && !SHADOW) {
             const unsigned act = __activemask();
             const unsigned leafM = __ballot_sync(act, leaf);
@@ -594,7 +602,7 @@ __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D
             if (SHADOW && best.pid != PID_NONE) break;
             visit = false;
         } else {
-            if (g & 0xFFu) { sstack[sp * sstride] = g; sp++; }
+            if (g & 0xFFu) { sts32(sbase + (uint32_t)sp * sstep, g); sp++; }
             node = ref;
             visit = true;
         }

@@ -29,8 +29,14 @@ def timed(rt, acc, spp, reps=3):
     return best
 
 
+WIDTHS = [2]
+
+
 def main():
-    specs = sys.argv[1:] or ["c3:256", "c5:64", "c4:64", "c2:64"]
+    args = sys.argv[1:]
+    if args and args[0].startswith("--widths="):
+        WIDTHS[:] = [int(x) for x in args.pop(0).split("=")[1].split(",")]
+    specs = args or ["c3:256", "c5:64", "c4:64", "c2:64"]
     out = []
     for spec in specs:
         name, spp = spec.split(":")[:2]
@@ -46,7 +52,8 @@ def main():
         rt.directLighting = bool(w.get("direct"))
         rt.setStream(torch.cuda.current_stream().cuda_stream)
         acc = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-        for sched in ("static",):
+        for sched in [("w%d" % x) for x in WIDTHS]:
+            rt.bvhWidth = int(sched[1:])                        # 2 = the binary LBVH, 4 / 8 = its wide collapse
             rt.countTests = False
             rt._push_params()
             ms = timed(rt, acc, spp)
@@ -59,7 +66,8 @@ def main():
             slots = 32 * st["trav_warp_iters"]
             row = dict(workload=name + (":d%d" % w["depth"]), spp=spp, schedule=sched, kernel_ms=ms, msamples_s=W * H * spp / ms / 1e3,
                        rays=st["rays"], rays_per_sample=st["rays"] / (W * H * spp),
-                       node_visits_per_ray=st["tests_aabb"] / 2 / max(1, st["rays"]),
+                       node_visits_per_ray=st["node_visits"] / max(1, st["rays"]), box_tests_per_ray=st["tests_aabb"] / max(1, st["rays"]),
+                       prim_tests_per_ray=(st["tests_sphere"] + st["tests_box"] + st["tests_tri_a"]) / max(1, st["rays"]),
                        trav_warp_iters=st["trav_warp_iters"],
                        frac_working=st["trav_lane_iters"] / max(1, slots),
                        frac_waiting=(st["trav_alive_lanes"] - st["trav_lane_iters"]) / max(1, slots),
@@ -77,9 +85,9 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "lane_attribution.json"), "w"), indent=1)
     with open(os.path.join(ROOT, "gpurun_out", "lane_attribution.md"), "w") as f:
-        f.write("| workload | spp | schedule | Msamples/s | working | waiting | drained | node-block issues / iter (lanes) | leaf-block issues / iter (lanes) | path-loop lanes |\n|---|---|---|---|---|---|---|---|---|---|\n")
+        f.write("| workload | spp | hierarchy | Msamples/s | node visits / ray | box tests / ray | primitive tests / ray | working | waiting | drained | node-block issues / iter (lanes) | leaf-block issues / iter (lanes) | path-loop lanes |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         for r in out:
-            f.write(f"| {r['workload']} | {r['spp']} | {r['schedule']} | {r['msamples_s']:.0f} | {r['frac_working']:.3f} | {r['frac_waiting']:.3f} | {r['frac_drained']:.3f} | "
+            f.write(f"| {r['workload']} | {r['spp']} | {r['schedule']} | {r['msamples_s']:.0f} | {r['node_visits_per_ray']:.2f} | {r['box_tests_per_ray']:.2f} | {r['prim_tests_per_ray']:.2f} | {r['frac_working']:.3f} | {r['frac_waiting']:.3f} | {r['frac_drained']:.3f} | "
                     f"{r['node_issue_frac']:.2f} ({r['lanes_per_node_issue']:.1f}) | {r['leaf_issue_frac']:.2f} ({r['lanes_per_leaf_issue']:.1f}) | {r['path_lanes_per_iter']:.1f} |\n")
 
 
