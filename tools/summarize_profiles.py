@@ -83,7 +83,7 @@ def ncu_summary(rep, dst, title):
 def sass_loop_excerpt(dst):
     """A trimmed cuobjdump -sass listing of the hot kernel's node-visit block (LDG.E.128 node loads, FFMA slabs, FMNMX / FMNMX3)."""
     obj = os.path.join(ROOT, "blenderraytracer_b200", "csrc", "build", "pathtrace.o")
-    fn = "_ZN3brt16k_pathtrace_megaILi0ELb1ELb0ELb0ELb0ELi1EEEvNS_8PTParamsE"
+    fn = "_ZN3brt16k_pathtrace_megaILi0ELb1ELb0ELb0ELb0ELi1ELi0EEEvNS_8PTParamsE"     # <fast, bvh, !count, !direct, !hybrid, PRIMS_SPHERE, binary>
     txt = subprocess.check_output(["cuobjdump", "-sass", "-fun", fn, obj], text=True)
     lines = [l for l in txt.splitlines() if "/*" in l and not l.strip().startswith("/* 0x")]
     lines = [l.split("/* 0x")[0].rstrip() for l in lines]
@@ -91,10 +91,11 @@ def sass_loop_excerpt(dst):
     lo = max(0, ix[0] - 40)
     while lo < ix[0] and "LDG.E.128" not in lines[lo]:
         lo += 1
-    hi = min(len(lines), ix[-1] + 30)
+    hi = min(len(lines), ix[-1] + 32)
     with open(dst, "w") as f:
         f.write("# cuobjdump -sass of k_pathtrace_mega<fast, bvh, PRIMS_SPHERE> (sm_100a): the node-visit block of the traversal loop\n"
-                "# (four 128-bit read-only loads of the 64-byte node, 12 FFMA slab planes, FMNMX / FMNMX3 reductions, near / far select, shared-memory push)\n")
+                "# (three 128-bit + one 64-bit read-only loads of the 64-byte centre / half-extent node, nine FFMA2 = the 18 slab planes of both children,\n"
+                "#  FMNMX3 / FMNMX reductions, one FMUL2 widening, near / far select, shared-memory push, sentinel pop)\n")
         f.write("\n".join(lines[max(0, lo - 3):hi]) + "\n")
 
 
