@@ -517,27 +517,52 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
 }
 
 // ------------------------------------------------------------------------------------------- wide hierarchy
-// N-wide (4 or 8) hierarchy collapsed from the binary tree (bvh.cu: k_wide_level).  A wide node is N / 2 PAIR RECORDS of 64 bytes,
-// each holding two child slots in exactly the layout of a centre / half-extent binary node (node_visit_ch):
-//   (cA.x, cB.x, cA.y, cB.y) (cA.z, cB.z, hA.x, hB.x) (hA.y, hB.y, hA.z, hB.z) (refA, refB, -, -)
-// ref = LEAF_BIT | pid, or the id of the child's wide node; an empty slot has h.x = -inf (near = +inf, far = -inf: never hit).
+// N-wide (4 or 8) hierarchy collapsed from the binary tree (bvh.cu: k_wide_level).  A wide node (32 N bytes) is N / 2 PAIR RECORDS of
+// 48 bytes, each holding two child slots in the box layout of a centre / half-extent binary node (node_visit_ch):
+//   (cA.x, cB.x, cA.y, cB.y) (cA.z, cB.z, hA.x, hB.x) (hA.y, hB.y, hA.z, hB.z)
+// followed by the N child refs (LEAF_BIT | pid, or the id of the child's wide node) as one contiguous uint32 array.  An empty slot
+// has h.x = -inf (near = +inf, far = -inf: never hit).
 // The boxes contain the binary tree's (padded) boxes and the slab arithmetic is pair_slabs — the same nine FFMA2 per TWO children
 // as the binary visit — so the wide traversal is as conservative as the binary one: same hits, same images.
 // Order: the builder puts a child into the slot whose index bits say on which side of the node's centre it lies (bit a set = the
 // + side of axis a; N = 8: x, y, z; N = 4: the tree's two widest axes).  XOR-ing the slot index with the ray's direction-sign bits
-// gives a front-to-back visiting order (Ylitie et al. 2017): the upper bits of that XOR are applied to the ADDRESS of the pair record
-// loaded in step k, the lowest bit by swapping adjacent bits of the hit mask, so mask bit j is "j-th nearest slot" and the next
-// child is simply the lowest set bit.  The stack holds one word per node that still has pending children (node id << 8 | pending
+// gives a front-to-back visiting order (Ylitie et al. 2017): the pair records are loaded in slot order (compile-time offsets from
+// one base register) and the hit mask is permuted into traversal order afterwards (wide_order), so mask bit j is "j-th nearest
+// slot" and the next child is simply the lowest set bit.  The stack holds one word per node that still has pending children (node id << 8 | pending
 // mask) — one entry per LEVEL, not per far child.
 // Measured on a B200 (profiles/r02_wide_hierarchy.md): the wide trees test the SAME number of boxes per ray as the binary tree at
-// N = 4 (C5 55.4 vs 55.7, C3 19.6 vs 18.8) in half the node visits (C5 14.2 vs 27.9, N = 8: 9.8), but a visit costs more than
-// N / 2 binary visits here — mask assembly, the pending-slot pick with its dependent ref load, the pair addressing — so the
-// binary walk stays faster on every config but the Cornell box (N = 4: C3 -13 %, C5 -4 %; N = 8: C3 -25 %, C5 -23 %, C4 +0.3 %).
+// N = 4 (C5 55.4 vs 55.7, C3 19.6 vs 18.8) in half the node visits (C5 14.2 vs 27.9, N = 8: 9.8), but the walk is slower on every
+// config but the Cornell box (N = 4: C3 -12 %, C5 -6 %; N = 8: C3 -20 %, C5 -23 %, C4 +0.6 %): only 4 % fewer warp-instructions
+// than the binary kernel on C5, two dependent loads per level (node, then the picked slot's ref), sparser nodes (L2 hit 91 % vs 99 %).
 // bvh_width = 0 (auto) therefore selects the binary tree; 4 / 8 stay selectable, with identical images.
+// Hit mask in slot order -> hit mask in traversal order (bit j = slot j ^ c).  N = 4: one 64-bit table per octant code, looked up
+// with a funnel shift (the 16 possible masks x 4 bits); N = 8: three conditional swaps of bit groups.
+__device__ __forceinline__ unsigned long long wide4_table(uint32_t c) {
+    // T_c = sum over the 16 masks m of perm_c(m) << 4m, perm_c(m) bit j = m bit (j ^ c); folded to a constant for a constant c
+    unsigned long long t = 0;
+#pragma unroll
+    for (uint32_t m = 0; m < 16; m++) {
+        uint32_t q = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) q |= ((m >> (j ^ c)) & 1u) << j;
+        t |= (unsigned long long)q << (4 * m);
+    }
+    return t;
+}
+template <int N>
+__device__ __forceinline__ uint32_t wide_order(uint32_t m, uint32_t c, unsigned long long table4) {
+    if (N == 4) return (uint32_t)(table4 >> (4u * m)) & 15u;
+    if (c & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+    if (c & 2u) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+    if (c & 4u) m = ((m & 0x0Fu) << 4) | ((m >> 4) & 0x0Fu);
+    return m;
+}
+
 template <int N, bool COUNT, bool SHADOW, int PRIMS = PRIMS_ANY>
 __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D, float tMin, float tMax, uint32_t self, Counters& cnt,
                                           uint32_t* sstack /* &smem[threadIdx.x] */, int sstride, unsigned aliveMask = 0xffffffffu) {
     static_assert(N == 4 || N == 8, "wide hierarchy: 4 or 8 children per node");
+    constexpr uint32_t STRIDE = 32u * N, REFS = 24u * N;             // node bytes; byte offset of the N child refs (after N / 2 pair records of 48 B)
     Hit best; best.t = tMax; best.pid = PID_NONE;
     test_planes<COUNT, SHADOW>(sc, O, D, tMin, self, best, cnt);
     if (sc.nNodes == 0) return best;
@@ -550,7 +575,12 @@ __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D
         const float d0 = a0 == 0 ? D.x : a0 == 1 ? D.y : D.z, d1 = a1 == 0 ? D.x : a1 == 1 ? D.y : D.z;
         c = (d0 < 0.f ? 1u : 0u) | (d1 < 0.f ? 2u : 0u);
     }
-    const uint32_t cp6 = (c >> 1) << 6;                // pair-record address XOR
+    unsigned long long table4 = 0;
+    if (N == 4) {
+        // the four tables are compile-time constants (wide4_table is evaluated per constant code); the ray keeps one of them
+        const unsigned long long t0 = wide4_table(0), t1 = wide4_table(1), t2 = wide4_table(2), t3 = wide4_table(3);
+        table4 = c == 0 ? t0 : c == 1 ? t1 : c == 2 ? t2 : t3;
+    }
     const char* const base = reinterpret_cast<const char*>(sc.wnodes);
     uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sstack);
     asm volatile("" : "+r"(sbase));
@@ -567,21 +597,19 @@ __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D
             }
         }
         if (visit) {
-            const char* np = base + (size_t)node * (32u * N);
+            const float4* np = reinterpret_cast<const float4*>(base + (size_t)node * STRIDE);
             uint32_t m = 0u;
             if (COUNT) cnt.nodeVisits++;
 #pragma unroll
-            for (int k = 0; k < N / 2; k++) {
-                const float4* pp = reinterpret_cast<const float4*>(np + ((((uint32_t)k) << 6) ^ cp6));
-                const float4 n0 = ldg4(pp), n1 = ldg4(pp + 1), n2 = ldg4(pp + 2);
+            for (int k = 0; k < N / 2; k++) {                          // pair records in SLOT order: compile-time offsets from one base
+                const float4 n0 = ldg4(np + 3 * k), n1 = ldg4(np + 3 * k + 1), n2 = ldg4(np + 3 * k + 2);
                 if (COUNT) cnt.aabb += (n1.z >= 0.f ? 1 : 0) + (n1.w >= 0.f ? 1 : 0);      // occupied slots
                 float tn0, tn1, tw0, tw1;
                 pair_slabs(n0, n1, n2, r, ainv, best.t, tn0, tn1, tw0, tw1);
                 if (tn0 <= tw0) m |= 1u << (2 * k);
                 if (tn1 <= tw1) m |= 2u << (2 * k);
             }
-            if (c & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
-            g = (node << 8) | m;
+            g = (node << 8) | wide_order<N>(m, c, table4);
         }
         if ((g & 0xFFu) == 0u) {
             if (sp == 0) break;
@@ -590,7 +618,7 @@ __device__ __forceinline__ Hit trace_wide(const DevScene& sc, float3 O, float3 D
         }
         const uint32_t slot = ((uint32_t)__ffs((int)g) - 1u) ^ c;          // the nearest pending slot (traversal order -> slot)
         g &= g - 1u;
-        const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(g >> 8) * (32u * N) + ((slot >> 1) << 6) + 48u + ((slot & 1u) << 2)));
+        const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(g >> 8) * STRIDE + REFS) + slot);
         const bool leaf = (ref & LEAF_BIT) != 0u;
         if (COUNT && !SHADOW) {
             const unsigned act = __activemask();

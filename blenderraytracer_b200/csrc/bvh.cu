@@ -405,29 +405,29 @@ __global__ void __launch_bounds__(128) k_wide_level(const float4* __restrict__ n
         }
         slotOf[bi] = bs; childAt[bs] = bi;
     }
-    // pair records: slots (2p, 2p + 1) share one 64-byte centre / half-extent record (node_visit_ch layout, children interleaved)
+    // node = N / 2 pair records of 48 bytes (slots 2p, 2p + 1 interleaved per axis: node_visit_ch's box layout) + the N refs
     float4* wp = wnodes + (size_t)b * (2 * N);
+    uint32_t* refs = reinterpret_cast<uint32_t*>(wp) + 6 * N;           // byte offset 24 N
     bool anyInternal = false;
     for (int pr = 0; pr < N / 2; pr++) {
-        float c[2][3], h[2][3]; uint32_t rf[2];
+        float c[2][3], h[2][3];
         for (int j = 0; j < 2; j++) {
             const int i = childAt[2 * pr + j];
             if (i < 0) {
                 // an empty slot: h.x = -inf makes the near plane +inf and the far plane -inf whatever the ray, so it is never hit
-                c[j][0] = c[j][1] = c[j][2] = 0.f; h[j][0] = -CUDART_INF_F; h[j][1] = h[j][2] = 0.f; rf[j] = 0xFFFFFFFFu;
+                c[j][0] = c[j][1] = c[j][2] = 0.f; h[j][0] = -CUDART_INF_F; h[j][1] = h[j][2] = 0.f; refs[2 * pr + j] = 0xFFFFFFFFu;
                 continue;
             }
             for (int a = 0; a < 3; a++) {
                 c[j][a] = 0.5f * lo[i][a] + 0.5f * hi[i][a];
                 h[j][a] = fmaxf(hi[i][a] - c[j][a], c[j][a] - lo[i][a]) * 1.0000005f + 1e-37f;     // as k_centre_half: [c - h, c + h] contains [lo, hi]
             }
-            rf[j] = ref[i];
+            refs[2 * pr + j] = ref[i];
             if (!(ref[i] & LEAF_BIT)) { levelOf[ref[i]] = level + 1; anyInternal = true; }
         }
-        wp[4 * pr + 0] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
-        wp[4 * pr + 1] = make_float4(c[0][2], c[1][2], h[0][0], h[1][0]);
-        wp[4 * pr + 2] = make_float4(h[0][1], h[1][1], h[0][2], h[1][2]);
-        wp[4 * pr + 3] = make_float4(__uint_as_float(rf[0]), __uint_as_float(rf[1]), 0.f, 0.f);
+        wp[3 * pr + 0] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
+        wp[3 * pr + 1] = make_float4(c[0][2], c[1][2], h[0][0], h[1][0]);
+        wp[3 * pr + 2] = make_float4(h[0][1], h[1][1], h[0][2], h[1][2]);
     }
     if (anyInternal) atomicMax(maxLevel, level + 1);
 }
@@ -492,10 +492,11 @@ cudaError_t build_wide(const BvhBuildResult& bin, int width, BvhWorkspace* ws, W
             nodesSeen++; deepest = std::max(deepest, d);
             if (id != 0 && lv[id] != d) bad++;
             for (int s2 = 0; s2 < width; s2++) {
-                const float4* rec = &h[(size_t)id * 2 * width + 4 * (s2 >> 1)];
-                const float hx = (s2 & 1) ? rec[1].w : rec[1].z, rb = (s2 & 1) ? rec[3].y : rec[3].x;
+                const float4* nodep = &h[(size_t)id * 2 * width];
+                const float4* rec = nodep + 3 * (s2 >> 1);
+                const float hx = (s2 & 1) ? rec[1].w : rec[1].z;
                 if (!(hx >= 0.f)) continue;
-                uint32_t r; memcpy(&r, &rb, 4);
+                uint32_t r; memcpy(&r, reinterpret_cast<const char*>(nodep) + 24 * width + 4 * s2, 4);
                 kids++;
                 if (r & LEAF_BIT) leaves++;
                 else if (r >= (uint32_t)nInternal) bad++;
