@@ -271,10 +271,16 @@ def test_render_params_validation(host):
     p = L.brt_render_params()
     assert lib.brt_get_render_params(h, C.byref(p)) == L.BRT_OK
     assert (p.width, p.height, p.spp, p.max_depth, p.gamma, p.exposure) == (600, 400, 4, 5, 2.2, 1.0)    # ray-tracer.js:19-30
-    for field, val in (("width", 0), ("height", -3), ("spp", 0), ("max_depth", -1), ("aa_mode", 9), ("tonemap", 5), ("sampler", 2), ("accel", 3)):
+    for field, val in (("width", 0), ("height", -3), ("spp", 0), ("max_depth", -1), ("aa_mode", 9), ("tonemap", 5), ("sampler", 2), ("accel", 3),
+                       ("bvh_width", 3), ("bvh_width", 16), ("bvh_width", -2)):
         q = L.brt_render_params(); C.memmove(C.byref(q), C.byref(p), C.sizeof(p))
         setattr(q, field, val)
         assert lib.brt_set_render_params(h, C.byref(q)) == L.BRT_E_INVALID, field
+    for w in (0, 2, 4, 8):                                           # 0 = auto; 2 = binary LBVH; 4 / 8 = its wide collapse
+        q = L.brt_render_params(); C.memmove(C.byref(q), C.byref(p), C.sizeof(p))
+        q.bvh_width = w
+        assert lib.brt_set_render_params(h, C.byref(q)) == L.BRT_OK, w
+    assert lib.brt_set_render_params(h, C.byref(p)) == L.BRT_OK
     assert lib.brt_set_background(h, 7, None, 1.0, None) == L.BRT_E_INVALID
     cam = L.brt_camera(); cam.type = 5
     assert lib.brt_set_camera(h, C.byref(cam)) == L.BRT_E_INVALID
