@@ -98,6 +98,7 @@ struct BvhWorkspace {            // grow-only build memory, owned by the ctx (fr
     float4* wide = nullptr; size_t wideCap = 0;         // wide hierarchy (build_wide)
     int* level = nullptr; size_t levelCap = 0;
     float4* cnodes = nullptr; size_t cnodeCap = 0;      // centre / half-extent copy of the chosen binary tree
+    void* host = nullptr; size_t hostCap = 0;           // pinned block the build's small results are copied into (asynchronously)
 };
 void free_bvh_workspace(BvhWorkspace* ws);
 struct BvhBuildResult {

@@ -274,40 +274,55 @@ __global__ void __launch_bounds__(256) k_sah_cost(const Aabb* nodeBox, int nInte
 // traversal (and therefore every result) is unchanged.
 constexpr int SAH_HOST_MAX = 16384;
 struct HostSah {
-    const std::vector<Aabb>& box; const std::vector<uint32_t>& pid;
-    std::vector<float4> nodes; std::vector<int> idx; double cost = 0.0; int depth = 0;
-    HostSah(const std::vector<Aabb>& b, const std::vector<uint32_t>& p) : box(b), pid(p) {}
+    const Aabb* box; const uint32_t* pid; int n;
+    std::vector<float4> nodes; double cost = 0.0;
+    // the primitives of the current range, sorted by centroid along each axis (presorted once, then stably partitioned at every
+    // split: O(n log n) for the whole build instead of four sorts per node)
+    std::vector<int> ord[3], tmp; std::vector<unsigned char> side; std::vector<double> right;
+    HostSah(const Aabb* b, const uint32_t* p, int count) : box(b), pid(p), n(count), tmp(count), side(count), right(count) {
+        for (int ax = 0; ax < 3; ax++) {
+            ord[ax].resize(n);
+            for (int i = 0; i < n; i++) ord[ax][i] = i;
+            std::stable_sort(ord[ax].begin(), ord[ax].end(), [&](int x, int y) { return box[x].mn[ax] + box[x].mx[ax] < box[y].mn[ax] + box[y].mx[ax]; });
+        }
+        nodes.reserve(4 * (size_t)(n > 1 ? n - 1 : 1));
+    }
     static double area(const Aabb& b) {
         double dx = (double)b.mx[0] - b.mn[0], dy = (double)b.mx[1] - b.mn[1], dz = (double)b.mx[2] - b.mn[2];
         return dx * dy + dy * dz + dz * dx;
     }
     static void grow(Aabb& a, const Aabb& b) { for (int k = 0; k < 3; k++) { a.mn[k] = std::min(a.mn[k], b.mn[k]); a.mx[k] = std::max(a.mx[k], b.mx[k]); } }
     static Aabb empty() { Aabb e; for (int k = 0; k < 3; k++) { e.mn[k] = FLT_MAX; e.mx[k] = -FLT_MAX; } return e; }
-    // builds the subtree over idx[lo, hi) (hi - lo >= 2); returns its node index, its box in `out`, its height in `h`
+    // builds the subtree over positions [lo, hi) of the three sorted lists (hi - lo >= 2; the same SET of primitives in each);
+    // returns its node index, its box in `out`, its height in `h`
     int build(int lo, int hi, Aabb& out, int& h) {
-        const int n = hi - lo, me = (int)(nodes.size() / 4);
+        const int m = hi - lo, me = (int)(nodes.size() / 4);
         nodes.resize(nodes.size() + 4);
-        int bestAxis = 0, bestK = n / 2; double bestC = DBL_MAX;
-        std::vector<double> right(n);
+        int bestAxis = 0, bestK = m / 2; double bestC = DBL_MAX;
         for (int ax = 0; ax < 3; ax++) {
-            std::stable_sort(idx.begin() + lo, idx.begin() + hi, [&](int a, int b) {
-                return box[a].mn[ax] + box[a].mx[ax] < box[b].mn[ax] + box[b].mx[ax]; });
+            const int* idx = ord[ax].data() + lo;
             Aabb acc = empty();
-            for (int k = n - 1; k >= 1; k--) { grow(acc, box[idx[lo + k]]); right[k] = area(acc); }
+            for (int k = m - 1; k >= 1; k--) { grow(acc, box[idx[k]]); right[k] = area(acc); }
             acc = empty();
-            for (int k = 1; k < n; k++) {
-                grow(acc, box[idx[lo + k - 1]]);
-                double c = area(acc) * k + right[k] * (n - k);
+            for (int k = 1; k < m; k++) {
+                grow(acc, box[idx[k - 1]]);
+                double c = area(acc) * k + right[k] * (m - k);
                 // ties (identical boxes) go to the most balanced split so duplicates cannot degenerate into a chain
-                if (c < bestC || (c == bestC && std::abs(k - n / 2) < std::abs(bestK - n / 2))) { bestC = c; bestAxis = ax; bestK = k; }
+                if (c < bestC || (c == bestC && std::abs(k - m / 2) < std::abs(bestK - m / 2))) { bestC = c; bestAxis = ax; bestK = k; }
             }
         }
-        std::stable_sort(idx.begin() + lo, idx.begin() + hi, [&](int a, int b) {
-            return box[a].mn[bestAxis] + box[a].mx[bestAxis] < box[b].mn[bestAxis] + box[b].mx[bestAxis]; });
+        for (int k = 0; k < m; k++) side[ord[bestAxis][lo + k]] = k < bestK ? 0 : 1;
+        for (int ax = 0; ax < 3; ax++) {
+            if (ax == bestAxis) continue;
+            int* idx = ord[ax].data() + lo;
+            int l = 0, r = 0;
+            for (int k = 0; k < m; k++) { if (side[idx[k]]) tmp[r++] = idx[k]; else idx[l++] = idx[k]; }
+            for (int k = 0; k < r; k++) idx[l + k] = tmp[k];
+        }
         Aabb cb[2]; uint32_t ref[2]; int ch[2] = { 0, 0 };
         const int range[2][2] = { { lo, lo + bestK }, { lo + bestK, hi } };
         for (int c = 0; c < 2; c++) {
-            if (range[c][1] - range[c][0] == 1) { int pi = idx[range[c][0]]; cb[c] = box[pi]; ref[c] = LEAF_BIT | pid[pi]; }
+            if (range[c][1] - range[c][0] == 1) { int pi = ord[0][range[c][0]]; cb[c] = box[pi]; ref[c] = LEAF_BIT | pid[pi]; }
             else { ref[c] = (uint32_t)build(range[c][0], range[c][1], cb[c], ch[c]); }
         }
         float4* np = &nodes[4 * (size_t)me];
@@ -514,6 +529,7 @@ cudaError_t build_wide(const BvhBuildResult& bin, int width, BvhWorkspace* ws, W
 void free_bvh_workspace(BvhWorkspace* ws) {
     if (!ws) return;
     cudaFree(ws->arena); cudaFree(ws->nodes[0]); cudaFree(ws->nodes[1]); cudaFree(ws->wide); cudaFree(ws->level); cudaFree(ws->cnodes);
+    if (ws->host) cudaFreeHost(ws->host);
     *ws = BvhWorkspace{};
 }
 
@@ -559,15 +575,38 @@ cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out
     int *parent = (int*)(A + oParent), *nodeDepth = (int*)(A + oDepth);
     double* blockSums = (double*)(A + oSums);
     float4 *nodes = ws->nodes[0], *nodesAlt = ws->nodes[1];
+    // results come back through ONE small pinned block (grow-only, owned by the workspace), so the copies are truly asynchronous:
+    //   [cost sums of candidate 0 | of candidate 1 | depth 0, depth 1 | scene bounds | padded boxes (small scenes only)]
+    const bool small = n <= SAH_HOST_MAX;
+    const size_t hSums = sizeof(double) * (size_t)costBlocks, hMisc = 2 * hSums, hBoxes = hMisc + 64;
+    const size_t hostBytes = hBoxes + (small ? sizeof(Aabb) * (size_t)n : 0);
+    if (hostBytes > ws->hostCap) {
+        if (ws->host) cudaFreeHost(ws->host);
+        ws->host = nullptr; ws->hostCap = 0;
+        BVH_CK(cudaHostAlloc(&ws->host, hostBytes, cudaHostAllocDefault));
+        ws->hostCap = hostBytes;
+    }
+    char* HB = (char*)ws->host;
+    double* hostSums[2] = { (double*)HB, (double*)(HB + hSums) };
+    int* hostDepth = (int*)(HB + hMisc);
+    float* hostSb = (float*)(HB + hMisc + 8);
+    const Aabb* hostBoxes = (const Aabb*)(HB + hBoxes);
+    cudaEvent_t eBoxes = nullptr;
     BVH_CK(cudaEventCreate(&e0)); BVH_CK(cudaEventCreate(&e1));
     BVH_CK(cudaEventRecord(e0, st));
     k_prim_bounds<<<nb, 256, 0, st>>>(sc, n, boxes, blockBounds);
     k_scene_bounds<<<1, 256, 0, st>>>(blockBounds, nb, sb);
-    // two candidate hierarchies (Morton quantisation per axis / uniform); the one with the smaller surface-area cost is kept
-    std::vector<double> hostSums(costBlocks);
-    double bestCost = 0.0; int bestMode = -1, bestDepth = 0;
-    float hostSb[6] = { 0, 0, 0, 0, 0, 0 };
-    for (int mode = 0; mode < 2; mode++) {
+    BVH_CK(cudaMemcpyAsync(hostSb, sb, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (small) {
+        BVH_CK(cudaMemcpyAsync((void*)hostBoxes, boxes, sizeof(Aabb) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (cudaEventCreateWithFlags(&eBoxes, cudaEventDisableTiming) != cudaSuccess) eBoxes = nullptr;
+        if (eBoxes) cudaEventRecord(eBoxes, st);
+    }
+    // two candidate hierarchies (Morton quantisation per axis / uniform), enqueued back to back without a host synchronisation:
+    // candidate 1 reuses the scratch arrays of candidate 0, whose results have been copied out in stream order by then.  Small
+    // scenes get the host SAH tree as their alternative instead of the uniform-scale LBVH (17 launches less on the e2e path).
+    const int nModes = small ? 1 : 2;
+    for (int mode = 0; mode < nModes; mode++) {
         float4* target = mode == 0 ? nodes : nodesAlt;
         k_morton<<<nb, 256, 0, st>>>(boxes, n, sb, mode, k0, v0);
         uint32_t *ki = k0, *ko = k1, *vi = v0, *vo = v1;
@@ -581,41 +620,51 @@ cudaError_t build_lbvh(const DevScene& sc, BvhWorkspace* ws, BvhBuildResult* out
         k_karras<<<(n - 1 + 255) / 256, 256, 0, st>>>(ki, n, children, parent);
         k_refit<<<nb, 256, 0, st>>>(sc, n, vi, boxes, children, parent, nodeBox, nodeDepth, flags, target);
         k_sah_cost<<<costBlocks, 256, 0, st>>>(nodeBox, n - 1, blockSums);
-        BVH_CK(cudaMemcpyAsync(hostSums.data(), blockSums, sizeof(double) * costBlocks, cudaMemcpyDeviceToHost, st));
-        int depth = 0;
-        BVH_CK(cudaMemcpyAsync(&depth, nodeDepth, 4, cudaMemcpyDeviceToHost, st));
-        if (mode == 0) BVH_CK(cudaMemcpyAsync(hostSb, sb, sizeof(hostSb), cudaMemcpyDeviceToHost, st));
-        BVH_CK(cudaStreamSynchronize(st));
+        BVH_CK(cudaMemcpyAsync(hostSums[mode], blockSums, hSums, cudaMemcpyDeviceToHost, st));
+        BVH_CK(cudaMemcpyAsync(hostDepth + mode, nodeDepth, 4, cudaMemcpyDeviceToHost, st));
+    }
+    // third candidate for small scenes, built on the host over the padded device boxes WHILE the GPU builds the other two
+    HostSah* sah = nullptr; int sahHeight = 0;
+    std::vector<uint32_t> pids;
+    if (small) {
+        cudaError_t e = eBoxes ? cudaEventSynchronize(eBoxes) : cudaStreamSynchronize(st);
+        if (eBoxes) cudaEventDestroy(eBoxes);
+        if (e != cudaSuccess) { cleanup(); return e; }
+        pids.resize(n);
+        for (int i = 0; i < n; i++) pids[i] = i < sc.nSph ? make_pid(PT_SPHERE, i) : i < sc.nSph + sc.nBox ? make_pid(PT_BOX, i - sc.nSph) : make_pid(PT_TRI, i - sc.nSph - sc.nBox);
+        sah = new HostSah(hostBoxes, pids.data(), n);
+        Aabb rootBox;
+        sah->build(0, n, rootBox, sahHeight);
+    }
+    {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { delete sah; cleanup(); return e; }
+    }
+    double bestCost = 0.0; int bestMode = -1, bestDepth = 0;
+    for (int mode = 0; mode < nModes; mode++) {
         double cost = 0.0;
-        for (double v : hostSums) cost += v;
-        if (getenv("BRT_DEBUG")) fprintf(stderr, "[brt] lbvh candidate %d: sah cost %.6g depth %d\n", mode, cost, depth);
+        for (int k = 0; k < costBlocks; k++) cost += hostSums[mode][k];                  // fixed order: deterministic choice
+        if (getenv("BRT_DEBUG")) fprintf(stderr, "[brt] lbvh candidate %d: sah cost %.6g depth %d\n", mode, cost, hostDepth[mode]);
         // the surface-area estimate assumes uniformly distributed rays; differences of a few percent are not predictive
         // (measured: C3 2 % apart, slower tree estimated cheaper), so the uniform-scale tree must win by > 10 % to be taken
-        if (bestMode < 0 || cost < 0.9 * bestCost) { bestCost = cost; bestMode = mode; bestDepth = depth; }
+        if (bestMode < 0 || cost < 0.9 * bestCost) { bestCost = cost; bestMode = mode; bestDepth = hostDepth[mode]; }
     }
     if (bestMode == 1) nodes = nodesAlt;
-    if (n <= SAH_HOST_MAX) {
-        // third candidate: host SAH over the padded device boxes (written into the node buffer the LBVH choice did not take)
-        std::vector<Aabb> hb(n);
-        BVH_CK(cudaMemcpyAsync(hb.data(), boxes, sizeof(Aabb) * n, cudaMemcpyDeviceToHost, st));
-        BVH_CK(cudaStreamSynchronize(st));
-        std::vector<uint32_t> pids(n);
-        for (int i = 0; i < n; i++) pids[i] = i < sc.nSph ? make_pid(PT_SPHERE, i) : i < sc.nSph + sc.nBox ? make_pid(PT_BOX, i - sc.nSph) : make_pid(PT_TRI, i - sc.nSph - sc.nBox);
-        HostSah sah(hb, pids);
-        sah.idx.resize(n);
-        for (int i = 0; i < n; i++) sah.idx[i] = i;
-        sah.nodes.reserve(4 * (size_t)(n - 1));
-        Aabb rootBox; int height = 0;
-        sah.build(0, n, rootBox, height);
-        if (getenv("BRT_DEBUG")) fprintf(stderr, "[brt] host sah candidate: sah cost %.6g depth %d\n", sah.cost, height);
+    if (sah) {
+        if (getenv("BRT_DEBUG")) fprintf(stderr, "[brt] host sah candidate: sah cost %.6g depth %d\n", sah->cost, sahHeight);
         const char* mg = getenv("BRT_SAH_MARGIN");
-        const double margin = mg ? atof(mg) : 0.9;
-        if (sah.cost < margin * bestCost && height <= SMEM_ONLY_MAX_DEPTH) {
+        // taken only when clearly cheaper: at 0.89 of the LBVH's cost (C3) the two trees render equally fast (6 355 vs 6 388
+        // Msamples/s), at 0.85 (the Cornell box) the SAH tree is 4 % faster
+        const double margin = mg ? atof(mg) : 0.88;
+        if (sah->cost < margin * bestCost && sahHeight <= SMEM_ONLY_MAX_DEPTH) {
+            // taken: written into the node buffer the LBVH choice did not take (pageable source: the copy is staged before the call returns)
             float4* target = nodes == ws->nodes[0] ? ws->nodes[1] : ws->nodes[0];
-            BVH_CK(cudaMemcpyAsync(target, sah.nodes.data(), sizeof(float4) * sah.nodes.size(), cudaMemcpyHostToDevice, st));
-            BVH_CK(cudaStreamSynchronize(st));
-            nodes = target; bestCost = sah.cost; bestDepth = height; bestMode = 2;
+            cudaError_t e = cudaMemcpyAsync(target, sah->nodes.data(), sizeof(float4) * sah->nodes.size(), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { delete sah; cleanup(); return e; }
+            nodes = target; bestCost = sah->cost; bestDepth = sahHeight; bestMode = 2;
         }
+        delete sah; sah = nullptr;
     }
     if (nodeBytes > ws->cnodeCap) {
         cudaFree(ws->cnodes); ws->cnodes = nullptr; ws->cnodeCap = 0;
