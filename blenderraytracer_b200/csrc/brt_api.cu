@@ -95,6 +95,8 @@ void brt_destroy(brt_ctx* ctx) {
                        &ctx->dAccum, &ctx->dRgba, &ctx->dFloat, &ctx->dFloat2, &ctx->dLinear, &ctx->dCounters, &ctx->dScratch, &ctx->dPlanes,
                        &ctx->dObj64, &ctx->dTris64 };
     for (DevBuf* b : bufs) b->release();
+    if (ctx->stagePending) { cudaEventSynchronize(ctx->evStage); ctx->stagePending = false; }
+    if (ctx->evStage) { cudaEventDestroy(ctx->evStage); ctx->evStage = nullptr; }
     ctx->hStage.release();
     free_bvh_workspace(&ctx->bvhWs);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -201,6 +203,19 @@ int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {
     return BRT_OK;
 }
 
+// The pinned staging buffer is written by the host and read by an asynchronous copy: an event marks the copy, and the next writer
+// (or whoever frees the buffer) waits for it — instead of a stream synchronisation inside every scene upload.
+static cudaError_t stage_mark(brt_ctx* ctx) {
+    if (!ctx->evStage) { cudaError_t e = cudaEventCreateWithFlags(&ctx->evStage, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    ctx->stagePending = true;
+    return cudaEventRecord(ctx->evStage, ctx->stream);
+}
+static cudaError_t stage_wait(brt_ctx* ctx) {
+    if (!ctx->stagePending) return cudaSuccess;
+    ctx->stagePending = false;
+    return cudaEventSynchronize(ctx->evStage);
+}
+
 static float4 f4(double x, double y, double z, double w) { return make_float4((float)x, (float)y, (float)z, (float)w); }
 
 // Flatten world.objects into per-type SoA float4 arrays + unified meta.  The arrays are written straight into ONE pinned
@@ -226,6 +241,7 @@ static int upload_scene(brt_ctx* ctx) {
     const size_t oSph = take(nSph * 16), oPln = take(nPln * 32), oBox = take(nBox * 32), oTri = take(nTri * 48), oMeta = take(nPrim * 16),
                  oMat = take(nMat * 16), oMatType = take(nMat * 4), oLights = take(nLights * 32), oTex = take(nTex * 32), oTexPerm = take(nTex * 512);
     const size_t arenaBytes = off;
+    CK(stage_wait(ctx));                                             // the previous upload may still be reading the staging buffer
     CK(ctx->hStage.ensure(arenaBytes));
     CK(ctx->dArena.ensure(arenaBytes));
     char* H = (char*)ctx->hStage.p;
@@ -290,7 +306,7 @@ static int upload_scene(brt_ctx* ctx) {
     d.nSph = (int)nSph; d.nPln = (int)nPln; d.nBox = (int)nBox; d.nTri = (int)nTri;
     d.nLights = (int)nLights; d.nTex = (int)nTex;
     if (arenaBytes) CK(cudaMemcpyAsync(ctx->dArena.p, H, arenaBytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));                         // the staging buffer is reused by the next upload
+    CK(stage_mark(ctx));                                             // no host synchronisation here: whoever writes the staging buffer next waits (stage_wait)
     const char* D = (const char*)ctx->dArena.p;
     d.sph = (const float4*)(D + oSph); d.pln = (const float4*)(D + oPln); d.box = (const float4*)(D + oBox); d.tri = (const float4*)(D + oTri);
     d.meta = (const int4*)(D + oMeta); d.mat = (const float4*)(D + oMat); d.matType = (const int*)(D + oMatType);
@@ -320,6 +336,7 @@ static int ensure_prim64(brt_ctx* ctx) {
     const HostScene& s = ctx->hostScene();
     const DevScene& d = ctx->dev;
     const size_t nPrim = (size_t)d.nSph + d.nPln + d.nBox + d.nTri;
+    CK(stage_wait(ctx));
     CK(ctx->hStage.ensure(nPrim * 72));
     CK(ctx->dPrim64.ensure(nPrim * 72));
     double* q = (double*)ctx->hStage.p;

@@ -58,6 +58,7 @@ struct brt_ctx {
     // device scene: one arena holding every SoA array (filled through one pinned staging buffer, one copy)
     DevBuf dArena, dPerm, dPrim64;
     PinnedBuf hStage;
+    cudaEvent_t evStage = nullptr; bool stagePending = false;   // marks the last asynchronous copy out of hStage
     brt::BvhWorkspace bvhWs;
     brt::BvhBuildResult bin{};                    // the binary hierarchy of the current scene
     brt::WideBuildResult wide{};                  // its wide collapse (built when a launch wants it)
