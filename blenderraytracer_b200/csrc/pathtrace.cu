@@ -7,6 +7,11 @@
 
 namespace brt {
 
+#ifndef MEGA_BLOCK
+#define MEGA_BLOCK PT_BLOCK            // threads per megakernel block: 16 x (MEGA_BLOCK / 16) pixels, one 8 x 4 sub-tile per warp
+                                       // (128 measured best on a B200: 64 threads x 16 blocks / SM -1.0 % C3, -3.0 % C5; 256 x 4 -2.5 %, -0.8 %)
+#endif
+
 // ------------------------------------------------------------------------------------------- the megakernel
 // One thread = one pixel, looping over its samples and regenerating a camera ray as soon as the current path ends, with a
 // blocking per-ray BVH traversal.  Measured against the warp-local wavefront (pathtrace_wave.cu) on the 1920x1080 random-spheres scene
@@ -19,11 +24,11 @@ namespace brt {
 // order-independent fixed-point tile sums in shared memory) cut the drained share only to 6 % — what remains is the random
 // spread of 256-sample sums, not a systematic difference between pixels — and lost 2 % to its bookkeeping; it was removed.
 template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID, int PRIMS = PRIMS_ANY, int WIDE = 0>
-__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega(const __grid_constant__ PTParams p) {
+__global__ void __launch_bounds__(MEGA_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega(const __grid_constant__ PTParams p) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int row = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int row = blockIdx.y * (MEGA_BLOCK / 16) + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = col < p.W && row < p.rowEnd && row >= p.rowBegin;
     const DevScene& sc = p.sc;
     // float64 primary rays + float64 evaluation of the primary hit: always with the sequential (reference) sampler — the mode
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                     O = tof3(O64); D = tof3(D64);
                     if (COUNT) cnt.rays++;
                     h.pid = PID_NONE; h.t = CUDART_INF_F;
-                    if (trace_primary64<USE_BVH, HYBRID>(sc, O64, D64, sstack, PT_BLOCK, h.pid, t64, sf)) h.t = (float)t64;
+                    if (trace_primary64<USE_BVH, HYBRID>(sc, O64, D64, sstack, MEGA_BLOCK, h.pid, t64, sf)) h.t = (float)t64;
                     primaryDone = true;
                 } else camera_ray32(p.cam32, p.W, p.H, p.aaMode, col, jUp, cam, O, D);
                 beta = f3(1.f, 1.f, 1.f); self = PID_NONE;
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                 aliveMask = __activemask();
                 if (lane == __ffs(aliveMask) - 1) { cnt.mainIter++; cnt.mainLanes += __popc(aliveMask); }
             }
-            if (!(PRECISE && primaryDone)) h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS, WIDE, CH>(sc, O, D, CUDART_INF_F, self, cnt, sstack, PT_BLOCK, aliveMask);
+            if (!(PRECISE && primaryDone)) h = trace<USE_BVH, COUNT, false, HYBRID, PRIMS, WIDE, CH>(sc, O, D, CUDART_INF_F, self, cnt, sstack, MEGA_BLOCK, aliveMask);
             if (h.pid == PID_NONE) {                                          // ray-tracer.js:122
                 sum = sum + beta * background(sc, D);
                 continue;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega
                     } else { ldir = f3(-l0.x, -l0.y, -l0.z); ldist = CUDART_INF_F; }
                     float cosN = dot(sf.N, ldir);
                     if (!(cosN > 0.f)) continue;
-                    Hit sh = trace<USE_BVH, COUNT, true, HYBRID, PRIMS_ANY, WIDE, CH>(sc, sf.P, ldir, ldist, h.pid, cnt, sstack, PT_BLOCK);
+                    Hit sh = trace<USE_BVH, COUNT, true, HYBRID, PRIMS_ANY, WIDE, CH>(sc, sf.P, ldir, ldist, h.pid, cnt, sstack, MEGA_BLOCK);
                     if (sh.pid != PID_NONE) continue;
                     sum = sum + beta * (f3(m.x, m.y, m.z) * lcol) * cosN;
                 }
@@ -203,18 +208,18 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, float 
 // the wide hierarchy: fast sampler only (the reference sampler decides primary visibility in float64 over the binary tree)
 template <int WIDE, bool COUNT, bool DIRECT>
 static cudaError_t launch_wide(const PTParams& p, dim3 grid, cudaStream_t st) {
-    const size_t smem = (size_t)(p.sc.wideDepth < 1 ? 1 : p.sc.wideDepth) * PT_BLOCK * sizeof(uint32_t);   // one entry per level
+    const size_t smem = (size_t)(p.sc.wideDepth < 1 ? 1 : p.sc.wideDepth) * MEGA_BLOCK * sizeof(uint32_t);   // one entry per level
     if constexpr (!COUNT && !DIRECT) {
-        if (p.sc.nBox == 0 && p.sc.nTri == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_SPHERE, WIDE><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
-        if (p.sc.nBox == 0 && p.sc.nSph == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_TRI, WIDE><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+        if (p.sc.nBox == 0 && p.sc.nTri == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_SPHERE, WIDE><<<grid, MEGA_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+        if (p.sc.nBox == 0 && p.sc.nSph == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_TRI, WIDE><<<grid, MEGA_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
     }
-    k_pathtrace_mega<0, true, COUNT, DIRECT, false, PRIMS_ANY, WIDE><<<grid, PT_BLOCK, smem, st>>>(p);
+    k_pathtrace_mega<0, true, COUNT, DIRECT, false, PRIMS_ANY, WIDE><<<grid, MEGA_BLOCK, smem, st>>>(p);
     return cudaGetLastError();
 }
 template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT>
 static cudaError_t launch_pt3(const PTParams& p, dim3 grid, cudaStream_t st) {
     if constexpr (!USE_BVH) {                              // brute force: no traversal stack at all
-        k_pathtrace_mega<SAMPLER, false, COUNT, DIRECT, false><<<grid, PT_BLOCK, 0, st>>>(p);
+        k_pathtrace_mega<SAMPLER, false, COUNT, DIRECT, false><<<grid, MEGA_BLOCK, 0, st>>>(p);
         return cudaGetLastError();
     } else {
         if constexpr (SAMPLER == 0) {
@@ -223,13 +228,13 @@ static cudaError_t launch_pt3(const PTParams& p, dim3 grid, cudaStream_t st) {
         }
         // the stack: depth + 1 entries per thread, all in shared memory, unless the tree is unusually deep
         const bool hybrid = p.sc.bvhStackDepth > SMEM_ONLY_MAX_DEPTH;
-        size_t smem = (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 2) * PT_BLOCK * sizeof(uint32_t);   // + the sentinel entry
-        if (hybrid) { k_pathtrace_mega<SAMPLER, true, COUNT, DIRECT, true><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+        size_t smem = (size_t)(hybrid ? SMEM_STACK : p.sc.bvhStackDepth + 2) * MEGA_BLOCK * sizeof(uint32_t);   // + the sentinel entry
+        if (hybrid) { k_pathtrace_mega<SAMPLER, true, COUNT, DIRECT, true><<<grid, MEGA_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
         if constexpr (SAMPLER == 0 && !COUNT && !DIRECT) {  // the common hot configurations get a leaf test without type dispatch
-            if (p.sc.nBox == 0 && p.sc.nTri == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_SPHERE><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
-            if (p.sc.nBox == 0 && p.sc.nSph == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_TRI><<<grid, PT_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+            if (p.sc.nBox == 0 && p.sc.nTri == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_SPHERE><<<grid, MEGA_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
+            if (p.sc.nBox == 0 && p.sc.nSph == 0) { k_pathtrace_mega<0, true, false, false, false, PRIMS_TRI><<<grid, MEGA_BLOCK, smem, st>>>(p); return cudaGetLastError(); }
         }
-        k_pathtrace_mega<SAMPLER, true, COUNT, DIRECT, false><<<grid, PT_BLOCK, smem, st>>>(p);
+        k_pathtrace_mega<SAMPLER, true, COUNT, DIRECT, false><<<grid, MEGA_BLOCK, smem, st>>>(p);
         return cudaGetLastError();
     }
 }
@@ -245,7 +250,7 @@ static cudaError_t launch_pt1(const PTParams& p, bool bvh, bool count, dim3 grid
 
 cudaError_t launch_pathtrace(const PTParams& p, int sampler, bool useBvh, bool count, int zSplit, cudaStream_t st) {
     if (p.wavefront && !count && p.maxDepth > 0) return launch_pathtrace_wave(p, sampler, useBvh, zSplit, st);
-    dim3 grid((p.W + 15) / 16, (p.H + 7) / 8, zSplit < 1 ? 1 : zSplit);
+    dim3 grid((p.W + 15) / 16, (p.H + MEGA_BLOCK / 16 - 1) / (MEGA_BLOCK / 16), zSplit < 1 ? 1 : zSplit);
     return sampler == 1 ? launch_pt1<1>(p, useBvh, count, grid, st) : launch_pt1<0>(p, useBvh, count, grid, st);
 }
 
