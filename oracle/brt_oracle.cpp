@@ -5,12 +5,12 @@
 // and bench.py's cpu_baseline / --impl reference legs may load this library;
 // the product (libbrt.so) never links, loads or calls it.
 //
-// PARITY STATUS: "parity unpinned by the reference" — the reference ships no
-// tests, golden vectors or fixtures beyond two sample scenes, and no JS engine
-// exists in this image, so the reference itself cannot be run here.  The
-// oracle is pinned instead against hand-derived float64 known-answer vectors
-// (tests/golden/) that follow the cited formulas, and cross-pinned bit for bit against a second,
-// independently written restatement (tests/golden/independent_port.py -> independent_vectors.npz).
+// PARITY STATUS: PINNED to the reference's own source.  The reference ships no tests or golden vectors and the image has
+// no JavaScript engine, so baseline/minijs.py (a small interpreter for the JavaScript subset the reference uses) executes the
+// UNMODIFIED js/*.js with Math.random replaced by this file's Philox stream; tests/test_reference_pin.py requires this oracle
+// to reproduce the resulting tests/golden/reference_vectors.json bit for bit (20 cases: radiance, floatData, RGBA8).  It is
+// also held by hand-derived float64 known-answer vectors (tests/golden/kat.json) and a second, independently written
+// restatement (tests/golden/independent_port.py -> independent_vectors.npz, bit for bit on 13 images).
 //
 // Every function cites the reference file:line it follows.  Arithmetic is
 // IEEE double with no FMA contraction (compile with -ffp-contract=off) because

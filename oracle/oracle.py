@@ -9,8 +9,9 @@ logic that sits above the per-pixel loop:
   updateBackground :568-585, resizeCanvas :598-614, loadCameraPreset :627-680, render :166-281)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this module.  PARITY UNPINNED by the reference (it ships no tests and cannot run here: no JS engine);
-pinned by hand-derived float64 known-answer vectors in tests/golden/.
+this module.  PARITY PINNED: tests/test_reference_pin.py compares it bit for bit with what the reference's own, unmodified
+js/*.js computes when executed by baseline/minijs.py (tests/golden/reference_vectors.json, 20 cases); also held by hand-derived
+float64 known-answer vectors and an independent second port (tests/golden/).
 """
 from __future__ import annotations
 

@@ -1,11 +1,18 @@
-"""Pins the oracle to the reference's OWN output, when that output is available.
+"""Pins the oracle to the reference's OWN output.
 
-tests/golden/reference_vectors.json is produced by running the UNMODIFIED reference (js/ray-tracer.js RayTracer.render) under
-Node with Math.random replaced by the oracle's Philox stream — `node baseline/make_fixtures.mjs` (see baseline/README.md).
-The build image has no JavaScript engine, so the file cannot be generated there: without it this test SKIPS with an explicit
-"parity unpinned" message and DESIGN.md says the same.  With it, every case must match the oracle: per-pixel mean radiance
-to 1e-12 relative (JS and C++ doubles agree exactly on + - * / sqrt; Math.tan / pow / exp / sin / cos may differ from glibc
-in the last ulp), RGBA8 within 1 LSB."""
+tests/golden/reference_vectors.json holds what the UNMODIFIED reference (js/ray-tracer.js RayTracer.render and everything it
+imports) computes for 20 cases with Math.random replaced by the oracle's Philox stream.  Two generators write that file:
+
+  * `python baseline/make_fixtures_minijs.py` — executes the reference's js/*.js through baseline/minijs.py, a small interpreter
+    for the JavaScript subset those files use (the build image has no JavaScript engine).  This is the committed file: Python
+    floats are IEEE doubles like JS Numbers and Math.* comes from the same C library the oracle links, so the comparison below is
+    BIT-EXACT (every per-pixel mean radiance, every gamma-corrected float, every RGBA8 byte).
+  * `node baseline/make_fixtures.mjs` — the same harness under Node.js / V8 (baseline/README.md), for whoever has Node: there
+    Math.tan / pow / exp / sin / cos may differ from glibc in the last ulp, so that variant is compared to 1e-12 relative / 1 LSB.
+
+The cases: the 13 of the second-port cross-check (both fixtures, the four presets, the four backgrounds, all AA / tone-map modes,
+denoise, the orthographic camera) + 7 shaped like the BASELINE configs (fixtures at depth 10, Cornell at depth 16 with ACES and
+denoise, thin-lens random spheres, a terrain mesh under the procedural sky, the duplicate / coplanar tie scene)."""
 import json
 import os
 
@@ -17,6 +24,25 @@ from oracle.oracle import OracleRayTracer
 
 VECTORS = os.path.join(GOLDEN, "reference_vectors.json")
 CASES = os.path.join(GOLDEN, "reference_cases.json")
+EXTRA = os.path.join(GOLDEN, "reference_cases_extra.json")
+
+
+def all_cases():
+    return json.load(open(CASES)) + (json.load(open(EXTRA)) if os.path.exists(EXTRA) else [])
+
+
+def oracle_render(c):
+    W, H = c["W"], c["H"]
+    rt = OracleRayTracer(W, H, seed=c["seed"], threads=2)
+    if "preset" in c:
+        rt.loadPreset(c["preset"])
+    else:
+        assert rt.loadFromJSON(c["scene"])
+    rt.setCloudPermutation(np.asarray(c["perm"], np.uint8))
+    rt.updateRenderSettings(dict(samples=c["spp"], maxBounces=c["depth"], antiAliasing=c["aa"], toneMapping=c["tonemap"],
+                                 exposure=c["exposure"], gamma=c["gamma"], denoising=c["denoise"], denoiseStrength=c["strength"]))
+    img = rt.render()
+    return rt, img
 
 
 def test_reference_cases_cover_the_second_port_cases():
@@ -33,22 +59,43 @@ def test_reference_cases_cover_the_second_port_cases():
 
 def test_oracle_matches_the_reference_itself():
     if not os.path.exists(VECTORS):
-        pytest.skip("PARITY UNPINNED: tests/golden/reference_vectors.json is absent — no JavaScript engine in this image; "
-                    "run `node baseline/make_fixtures.mjs` where Node.js exists (baseline/README.md)")
-    ref = json.load(open(VECTORS))["cases"]
-    for c in json.load(open(CASES)):
+        pytest.skip("PARITY UNPINNED: tests/golden/reference_vectors.json is absent — run `python baseline/make_fixtures_minijs.py` "
+                    "(or `node baseline/make_fixtures.mjs` where Node.js exists, baseline/README.md)")
+    doc = json.load(open(VECTORS))
+    ref, exact = doc["cases"], "minijs" in doc.get("generator", "")
+    cases = all_cases()
+    assert len(cases) >= 20 and all(c["name"] in ref for c in cases), sorted(set(c["name"] for c in cases) - set(ref))
+    for c in cases:
         name, W, H = c["name"], c["W"], c["H"]
         want = ref[name]
-        rt = OracleRayTracer(W, H, seed=c["seed"], threads=2)
-        if "preset" in c:
-            rt.loadPreset(c["preset"])
-        else:
-            assert rt.loadFromJSON(c["scene"])
-        rt.setCloudPermutation(np.asarray(c["perm"], np.uint8))
-        rt.updateRenderSettings(dict(samples=c["spp"], maxBounces=c["depth"], antiAliasing=c["aa"], toneMapping=c["tonemap"],
-                                     exposure=c["exposure"], gamma=c["gamma"], denoising=c["denoise"], denoiseStrength=c["strength"]))
-        img = rt.render()
+        rt, img = oracle_render(c)
         lin = np.asarray(want["linear"], np.float64).reshape(H, W, 3)
-        np.testing.assert_allclose(rt.linear[..., :3], lin, rtol=1e-12, atol=1e-15, err_msg=name)
+        fdat = np.asarray(want["float"], np.float64).reshape(H, W, 3)
         rgba = np.asarray(want["rgba"], np.uint8).reshape(H, W, 4)
-        assert np.abs(img.astype(int) - rgba.astype(int)).max() <= 1, name
+        assert np.isfinite(lin).all() and lin.max() > 0, name
+        if exact:
+            # same arithmetic, same libm: the oracle must reproduce the reference's own numbers bit for bit
+            assert np.array_equal(rt.linear[..., :3], lin), (name, int((rt.linear[..., :3] != lin).sum()))
+            assert np.array_equal(rt.floatData[..., :3], fdat.astype(np.float32)), name      # floatData is a Float32Array (ray-tracer.js:186)
+            assert np.array_equal(img, rgba), (name, int((img != rgba).sum()))
+        else:
+            np.testing.assert_allclose(rt.linear[..., :3], lin, rtol=1e-12, atol=1e-15, err_msg=name)
+            assert np.abs(img.astype(int) - rgba.astype(int)).max() <= 1, name
+        assert (rgba[..., 3] == 255).all(), name
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine (the GPU box): the committed vectors are used")
+def test_committed_vectors_are_what_the_reference_source_computes():
+    """Where the reference checkout exists, two cases are re-executed from its js/*.js and must reproduce the committed vectors."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "baseline"))
+    import make_fixtures_minijs as M
+    sys.setrecursionlimit(20000)
+    doc = json.load(open(VECTORS))
+    assert "minijs" in doc["generator"]
+    by_name = {c["name"]: c for c in all_cases()}
+    for name in ("bg_procedural_sky", "preset_glass"):
+        interp, RayTracer, Vec3 = M.load_reference("/root/reference/js")
+        got = M.render_seeded(interp, RayTracer, Vec3, by_name[name])
+        want = doc["cases"][name]
+        assert got["rgba"] == want["rgba"] and got["linear"] == want["linear"] and got["float"] == want["float"], name
