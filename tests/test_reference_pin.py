@@ -99,3 +99,40 @@ def test_committed_vectors_are_what_the_reference_source_computes():
         got = M.render_seeded(interp, RayTracer, Vec3, by_name[name])
         want = doc["cases"][name]
         assert got["rgba"] == want["rgba"] and got["linear"] == want["linear"] and got["float"] == want["float"], name
+
+
+TEX_VECTORS = os.path.join(GOLDEN, "reference_texture_vectors.json")
+
+
+def test_oracle_textures_match_the_reference():
+    """js/textures.js + js/noise.js + TexturedLambertian / TexturedMetal (js/materials.js:99-126), executed from the reference's
+    source by baseline/minijs.py (baseline/make_texture_fixtures_minijs.py): texture values at 48 points per texture and one
+    seeded render through the textured materials — the oracle's restatement must give the same bits."""
+    doc = json.load(open(TEX_VECTORS))
+    assert "minijs" in doc["generator"]
+    pts = doc["points"]
+    for t in doc["textures"]:
+        rt = OracleRayTracer(8, 8)
+        sc = rt.scene
+        sc.add_sphere((0, 0, 0), 1.0, ("lambertian", [1, 1, 1], 0.0))
+        sc.set_object_texture(0, t["kind"], tuple(t["odd"]), tuple(t["even"]), t["scale"], perm256=t["perm"])
+        got = np.array([sc.texture_value(0, p) for p in pts])
+        want = np.asarray(t["values"], np.float64)
+        assert np.array_equal(got, want), (t["name"], int((got != want).sum()), np.abs(got - want).max())
+    r = doc["render"]
+    c = r["case"]
+    by_name = {t["name"]: t for t in doc["textures"]}
+    rt = OracleRayTracer(c["W"], c["H"], seed=c["seed"], threads=2)
+    assert rt.loadFromJSON(c["scene"])
+    rt.setCloudPermutation(np.asarray(c["perm"], np.uint8))
+    for obj, name in r["textured_objects"].items():
+        t = by_name[name]
+        rt.scene.set_object_texture(int(obj), t["kind"], tuple(t["odd"]), tuple(t["even"]), t["scale"], perm256=t["perm"])
+    assert len(r["textured_objects"]) >= 3
+    rt.updateRenderSettings(dict(samples=c["spp"], maxBounces=c["depth"], antiAliasing=c["aa"], toneMapping=c["tonemap"], exposure=c["exposure"],
+                                 gamma=c["gamma"], denoising=c["denoise"], denoiseStrength=c["strength"]))
+    img = rt.render()
+    W, H = c["W"], c["H"]
+    lin = np.asarray(r["linear"], np.float64).reshape(H, W, 3)
+    assert np.array_equal(rt.linear[..., :3], lin), int((rt.linear[..., :3] != lin).sum())
+    assert np.array_equal(img, np.asarray(r["rgba"], np.uint8).reshape(H, W, 4))
