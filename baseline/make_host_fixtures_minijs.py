@@ -151,6 +151,23 @@ def main():
             steps.append(dict(ok=ok, state=dump_state(rt)))
         out["cases"].append(dict(name=c["name"], W=c["W"], H=c["H"], scenes=c["scenes"], steps=steps))
         print(c["name"], [s["ok"] for s in steps], len(steps[-1]["state"]["objects"]), "objects")
+    # lights.js illuminate() — never called by the reference's render loop (the direct-lighting EXTENSION uses its formulas)
+    interp, RayTracer, Vec3 = M.load_reference(js_dir)
+    lights_ex = interp.load_module(os.path.join(js_dir, "lights.js"))
+    v = lambda c: interp.construct(Vec3, [float(c[0]), float(c[1]), float(c[2])])
+    specs = [dict(kind="point", v=[1.0, 4.0, -2.5], color=[1.0, 0.9, 0.8], intensity=12.0), dict(kind="point", v=[0.0, 0.0, 0.0], color=[0.2, 0.4, 0.6], intensity=1.0),
+             dict(kind="directional", v=[0.3, -1.0, 0.2], color=[1.0, 1.0, 0.9], intensity=2.5)]
+    pts = [[0.0, 0.0, 0.0], [1.0, 4.0, -2.5], [0.5, -0.5, 3.0], [-7.25, 2.125, 0.001], [100.0, -50.0, 25.0]]
+    out["lights"] = []
+    for sp in specs:
+        cls = lights_ex["PointLight" if sp["kind"] == "point" else "DirectionalLight"]
+        light = interp.construct(cls, [v(sp["v"]), v(sp["color"]), float(sp["intensity"])])
+        rows = []
+        for p in pts:
+            r = interp.call(light.get("illuminate"), light, [v(p)])
+            rows.append(dict(direction=vec(r.get("direction")), color=vec(r.get("color")), distance=(None if r.get("distance") == float("inf") else r.get("distance"))))
+        out["lights"].append(dict(sp, points=pts, illuminate=rows))
+    print("lights:", len(out["lights"]))
     json.dump(out, open(args.out, "w"))
     print("wrote", args.out)
 

@@ -126,10 +126,29 @@ def test_native_ingest_equals_the_reference_loader(host):
             lib.brt_destroy(h)
 
 
+def test_oracle_lights_match_the_reference():
+    """lights.js illuminate() (js/lights.js:22-47; dead code in the reference's render loop, the formulas of the direct-lighting
+    extension) executed from the reference's source, against the oracle's restatement: exact doubles."""
+    from oracle.oracle import OracleRayTracer, _d3
+    doc = json.load(open(VECTORS))
+    assert len(doc["lights"]) >= 3
+    for sp in doc["lights"]:
+        sc = OracleRayTracer(8, 8).scene
+        (sc.add_point_light if sp["kind"] == "point" else sc.add_directional_light)(sp["v"], sp["color"], sp["intensity"])
+        idx = len(sc.lights_log) - 1                                       # after the default scene's own lights (ray-tracer.js:42-77)
+        for p, want in zip(sp["points"], sp["illuminate"]):
+            out = (C.c_double * 7)()
+            sc.L.orc_illuminate(sc.h, idx, _d3(p), out)
+            got = list(out)
+            eq(got[0:3], want["direction"], "direction"); eq(got[3:6], want["color"], "colour")
+            assert got[6] == (float("inf") if want["distance"] is None else want["distance"])
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine")
 def test_committed_host_vectors_are_what_the_reference_source_computes(tmp_path):
     import subprocess, sys
     out = tmp_path / "host.json"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.check_call([sys.executable, os.path.join(root, "baseline", "make_host_fixtures_minijs.py"), "--out", str(out)], stdout=subprocess.DEVNULL)
-    assert json.load(open(out))["cases"] == json.load(open(VECTORS))["cases"]
+    new, old = json.load(open(out)), json.load(open(VECTORS))
+    assert new["cases"] == old["cases"] and new["lights"] == old["lights"]
