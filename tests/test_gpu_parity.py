@@ -692,3 +692,31 @@ def test_gpu_tracks_the_reference_vectors_sample_for_sample(brt):
         assert (img[..., 3] == 255).all()
         rt.close()
     assert np.mean([v[1] for v in worst.values()]) >= 0.999, worst
+
+
+def test_gpu_primary_visibility_equals_the_reference(brt):
+    """North-star gate "primary-hit object IDs bit-exact" against the reference ITSELF: camera.getRay + World.hit of the unmodified
+    js/*.js at every pixel centre (tests/golden/reference_aov_vectors.json, baseline/make_aov_fixtures_minijs.py) vs the float64
+    AOV kernel (IDs, t, normal, frontFace exact) and vs the render path's own primary-hit code (IDs exact, t to fp32 rounding),
+    with the linear loops and with the hierarchy."""
+    doc = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_aov_vectors.json")))
+    for c in doc["cases"]:
+        H, W = c["H"], c["W"]
+        want_obj = np.asarray(c["obj_id"], np.int32).reshape(H, W); want_tri = np.asarray(c["tri_id"], np.int32).reshape(H, W)
+        want_t = np.array([np.inf if v is None else v for v in c["t"]], np.float64).reshape(H, W)
+        want_n = np.asarray(c["normal"], np.float64).reshape(H, W, 3); want_ff = np.asarray(c["front_face"], np.uint8).reshape(H, W)
+        hit = want_obj >= 0
+        rt = brt.RayTracer(W, H, seed=1)
+        assert rt.loadFromJSON(c["scene"])
+        a64 = rt.primaryAOV(64)
+        assert np.array_equal(a64["obj_id"], want_obj) and np.array_equal(a64["tri_id"], want_tri), c["name"]
+        assert np.array_equal(a64["t"][hit], want_t[hit]) and np.array_equal(a64["normal"][hit], want_n[hit]), c["name"]
+        assert np.array_equal(a64["front_face"][hit], want_ff[hit]), c["name"]
+        for accel in ("brute", "bvh"):
+            rt.accel = accel
+            a = rt.primaryAOV(32)
+            assert np.array_equal(a["obj_id"], want_obj) and np.array_equal(a["tri_id"], want_tri), (c["name"], accel, int((a["obj_id"] != want_obj).sum()))
+            assert np.array_equal(a["t"][hit], want_t[hit].astype(np.float32)), (c["name"], accel)       # the float64 t, rounded once
+            assert np.array_equal(a["front_face"][hit], want_ff[hit]), (c["name"], accel)
+            np.testing.assert_allclose(a["normal"][hit], want_n[hit], rtol=0, atol=2e-7, err_msg=c["name"])
+        rt.close()

@@ -136,3 +136,32 @@ def test_oracle_textures_match_the_reference():
     lin = np.asarray(r["linear"], np.float64).reshape(H, W, 3)
     assert np.array_equal(rt.linear[..., :3], lin), int((rt.linear[..., :3] != lin).sum())
     assert np.array_equal(img, np.asarray(r["rgba"], np.uint8).reshape(H, W, 4))
+
+
+AOV_VECTORS = os.path.join(GOLDEN, "reference_aov_vectors.json")
+
+
+def reference_aov(c):
+    H, W = c["H"], c["W"]
+    t = np.array([np.inf if v is None else v for v in c["t"]], np.float64).reshape(H, W)
+    return dict(obj_id=np.asarray(c["obj_id"], np.int32).reshape(H, W), tri_id=np.asarray(c["tri_id"], np.int32).reshape(H, W), t=t,
+                normal=np.asarray(c["normal"], np.float64).reshape(H, W, 3), front_face=np.asarray(c["front_face"], np.uint8).reshape(H, W))
+
+
+def test_oracle_primary_visibility_matches_the_reference():
+    """North-star gate "primary-hit object IDs bit-exact", against the reference itself: camera.getRay + World.hit of the unmodified
+    js/*.js at every pixel centre (baseline/make_aov_fixtures_minijs.py) vs the oracle — object and triangle IDs, t, normal,
+    frontFace: exact, incl. the duplicate / coplanar tie scene (first object wins, last triangle of a mesh wins)."""
+    doc = json.load(open(AOV_VECTORS))
+    assert "minijs" in doc["generator"] and len(doc["cases"]) >= 6
+    for c in doc["cases"]:
+        rt = OracleRayTracer(c["W"], c["H"])
+        assert rt.loadFromJSON(c["scene"])
+        got, want = rt.primary_aov(), reference_aov(c)
+        hit = want["obj_id"] >= 0
+        assert hit.sum() > 500, c["name"]
+        assert np.array_equal(got["obj_id"], want["obj_id"]), (c["name"], int((got["obj_id"] != want["obj_id"]).sum()))
+        assert np.array_equal(got["tri_id"], want["tri_id"]), (c["name"], int((got["tri_id"] != want["tri_id"]).sum()))
+        assert np.array_equal(got["t"][hit], want["t"][hit]), c["name"]
+        assert np.array_equal(got["normal"][hit], want["normal"][hit]), c["name"]
+        assert np.array_equal(got["front_face"][hit], want["front_face"][hit]), c["name"]
