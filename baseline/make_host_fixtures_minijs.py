@@ -134,6 +134,62 @@ def cases():
     return out
 
 
+def control_calls():
+    """A session at the reference's control surface (ray-tracer.js:439-614, 627-680): every camera preset and an unknown one, partial
+    updateCamera calls that exercise each `||` fallback (0 and absent mean "keep"), setCameraPosition with and without arguments,
+    resizes (setupCamera rebuilds the camera from its own derived vectors), every background kind."""
+    calls = [["loadCameraPreset", n] for n in ("close-up", "wide-angle", "top-down", "side-view", "default", "no-such-preset")]
+    calls += [["updateCamera", dict(fov=30)], ["updateCamera", dict(position=[1, 2, 3])], ["updateCamera", dict(aperture=0.1, focusDist=3)],
+              ["updateCamera", dict(type="orthographic")], ["updateCamera", dict(fov=0, aperture=0, focusDist=0)],
+              ["updateCamera", dict(up=[0, 0, 1], lookAt=[1, 1, 1], type="perspective")], ["updateCamera", dict()],
+              ["resizeCanvas", 800, 450], ["resizeCanvas", 333, 777], ["setCameraPosition", [4, 1, -2], None, None],
+              ["setCameraPosition", None, [0, 0.5, 0], [0, 1, 0]], ["setCameraPosition", None, None, None], ["resizeCanvas", 600, 400],
+              ["updateCamera", dict(position=[0, 0, 5], lookAt=[0, 0, 0], up=[0, 1, 0], fov=90, aperture=2, focusDist=5)], ["getCameraPosition"]]
+    calls += [["updateBackground", k, i] for k, i in (("solid", 0.5), ("hdri", 2.0), ("procedural_sky", 0.25), ("gradient", 3.0), ("weird", 1.5))]
+    calls += [["updateBackground", "solid"], ["loadPreset", "cornell"], ["loadCameraPreset", "close-up"], ["resizeCanvas", 512, 512]]
+    return calls
+
+
+PROBE_PERM = [(i * 167 + 13) % 256 for i in range(256)]          # a fixed permutation of 0..255 (167 is odd)
+PROBE_DIRS = [[0.0, 1.0, 0.0], [0.0, -1.0, 0.0], [0.3, 0.6, 0.8], [-0.3, 0.6, -0.5], [1.0, 0.05, -0.2], [-0.7, 0.2, 0.4]]
+
+
+def run_controls(interp, RayTracer, Vec3, Ray):
+    rt = interp.construct(RayTracer, [M.fake_canvas(interp, 600, 400)])
+    v = lambda c: J.UNDEF if c is None else interp.construct(Vec3, [float(c[0]), float(c[1]), float(c[2])])
+    def view(ret=None):
+        st = dump_state(rt)
+        world = rt.get("world")
+        # world.background evaluated on fixed rays: says which background is installed (solid / hdri are anonymous closures,
+        # world.js:42-44, 74-111) and with which intensity; the cloud table (random per World, noise.js:7-17) is an input here as in
+        # the render cases
+        p = world.get("cloudNoise").get("p")
+        for i in range(256):
+            J.set_member(p, float(i), float(PROBE_PERM[i])); J.set_member(p, float(256 + i), float(PROBE_PERM[i]))
+        probe = []
+        for d in PROBE_DIRS:
+            probe.append(vec(interp.call(world.get("background"), world, [interp.construct(Ray, [v([0, 0, 0]), v(d)])])))
+        kind = {"bound skyGradient": "gradient", "bound proceduralSky": "procedural_sky"}.get(st["background"])
+        if kind is None:
+            kind = "solid" if probe[0] == probe[1] == probe[4] else "hdri"
+        return dict(camera=st["camera"], background=kind, bgProbe=probe, skyIntensity=st["skyIntensity"], width=st["width"], height=st["height"],
+                    n_objects=len(st["objects"]), ret=ret)
+    steps = [dict(call=["constructor"], state=view())]
+    for call in control_calls():
+        name, args = call[0], call[1:]
+        if name == "setCameraPosition":
+            ret = M.method(interp, rt, name, *[v(a) for a in args])
+        else:
+            ret = M.method(interp, rt, name, *[J.py_to_js(a) if isinstance(a, (dict, list)) else (float(a) if isinstance(a, (int, float)) else a) for a in args])
+        if name == "getCameraPosition":
+            ret = dict(position=vec(ret.get("position")), lookAt=vec(ret.get("lookAt")), up=vec(ret.get("up")), fov=ret.get("fov"),
+                       aperture=ret.get("aperture"), focusDist=ret.get("focusDist"), type=ret.get("type"))
+        else:
+            ret = ret if isinstance(ret, bool) else None
+        steps.append(dict(call=call, state=view(ret)))
+    return steps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default=os.environ.get("BRT_REFERENCE", "/root/reference"))
@@ -168,6 +224,10 @@ def main():
             rows.append(dict(direction=vec(r.get("direction")), color=vec(r.get("color")), distance=(None if r.get("distance") == float("inf") else r.get("distance"))))
         out["lights"].append(dict(sp, points=pts, illuminate=rows))
     print("lights:", len(out["lights"]))
+    interp, RayTracer, Vec3 = M.load_reference(js_dir)
+    out["controls"] = run_controls(interp, RayTracer, Vec3, interp.load_module(os.path.join(js_dir, "math.js"))["Ray"])
+    out["probe_dirs"], out["probe_perm"] = PROBE_DIRS, PROBE_PERM
+    print("controls:", len(out["controls"]), "steps")
     json.dump(out, open(args.out, "w"))
     print("wrote", args.out)
 

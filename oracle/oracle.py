@@ -588,6 +588,21 @@ class OracleRayTracer:
                               pick("aperture", "aperture", 0.0), pick("focusDist", "focusDist", 10.0),
                               pick("type", "type", "perspective"))
 
+    def setCameraPosition(self, lookFrom=None, lookAt=None, vup=None):  # :515-535
+        if not self.scene.has_camera:
+            self.scene.set_camera(lookFrom if lookFrom is not None else (3, 2, 2), lookAt if lookAt is not None else (0, 0, -1),
+                                  vup if vup is not None else (0, 1, 0), 45, self.width / self.height, 0.0, 10.0, "perspective")
+        else:
+            self.updateCamera({"position": None if lookFrom is None else list(lookFrom), "lookAt": None if lookAt is None else list(lookAt),
+                               "up": None if vup is None else list(vup)})
+
+    def getCameraPosition(self):                                       # :540-552
+        if not self.scene.has_camera:
+            return None
+        c = self.scene.camera()
+        return dict(position=c["origin"], lookAt=c["origin"] - c["w"] * c["focusDist"], up=c["v"], fov=c["fov"], aperture=c["aperture"],
+                    focusDist=c["focusDist"], type=c["type"])
+
     def loadCameraPreset(self, name) -> bool:                          # :627-680
         presets = {
             "default": dict(position=[3, 2, 2], lookAt=[0, 0, -1], up=[0, 1, 0], fov=45, aperture=0.0, focusDist=10.0),

@@ -151,4 +151,69 @@ def test_committed_host_vectors_are_what_the_reference_source_computes(tmp_path)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.check_call([sys.executable, os.path.join(root, "baseline", "make_host_fixtures_minijs.py"), "--out", str(out)], stdout=subprocess.DEVNULL)
     new, old = json.load(open(out)), json.load(open(VECTORS))
-    assert new["cases"] == old["cases"] and new["lights"] == old["lights"]
+    assert new["cases"] == old["cases"] and new["lights"] == old["lights"] and new["controls"] == old["controls"]
+
+
+def _controls_session(rt, cam_view, doc):
+    """replays doc["controls"] on `rt` (an object with the reference's method names); cam_view(rt) -> dict of camera fields"""
+    steps = doc["controls"]
+    assert len(steps) >= 30 and steps[0]["call"] == ["constructor"]
+    for k, st in enumerate(steps):
+        call = st["call"]
+        name, args = call[0], call[1:]
+        ret = None
+        if name != "constructor":
+            if name == "setCameraPosition":
+                args = [None if a is None else np.asarray(a, np.float64) for a in args]
+            ret = getattr(rt, name)(*args)
+        want, what = st["state"], f"controls step {k} {call}"
+        assert (rt.width, rt.height) == (want["width"], want["height"]), what
+        cam, rc = cam_view(rt), want["camera"]
+        for key in ("origin", "lowerLeftCorner", "horizontal", "vertical", "u", "v", "w"):
+            eq(cam[key], rc[key], f"{what} camera.{key}")
+        assert (cam["lensRadius"], cam["fov"], cam["aperture"], cam["focusDist"], cam["type"]) == \
+               (rc["lensRadius"], rc["fov"], rc["aperture"], rc["focusDist"], rc["type"]), what
+        if name == "loadCameraPreset":
+            assert ret is want["ret"], what
+        if name == "getCameraPosition":
+            for key in ("position", "lookAt", "up"):
+                eq(ret[key], want["ret"][key], f"{what} {key}")
+            assert (ret["fov"], ret["aperture"], ret["focusDist"], ret["type"]) == tuple(want["ret"][k2] for k2 in ("fov", "aperture", "focusDist", "type")), what
+        yield st, what
+
+
+def test_python_mirror_controls_equal_the_reference(host):
+    """The reference's control surface above the C ABI — loadCameraPreset / updateCamera / setCameraPosition / getCameraPosition /
+    resizeCanvas -> setupCamera / updateBackground / loadPreset (ray-tracer.js:282-299, 439-614, 627-680) — replayed on the Python
+    mirror over a host-only libbrt context: after each of 31 calls the camera libbrt holds, the canvas size, the background kind
+    and sky intensity are what the reference's own objects hold (exact doubles)."""
+    lib, _ = host
+    doc = json.load(open(VECTORS))
+    rt = brt.RayTracer(600, 400, device=-1)
+    try:
+        def cam_view(r):
+            c = r.camera
+            return dict(c, lensRadius=c["lensRadius"])
+        for st, what in _controls_session(rt, cam_view, doc):
+            want = st["state"]
+            kind, col, inten = C.c_int(), (C.c_double * 3)(), C.c_double()
+            lib.brt_get_background(rt._ctx, C.byref(kind), col, C.byref(inten))
+            assert kind.value == L.BG[want["background"]] and inten.value == want["skyIntensity"], what
+            assert len(_flat(lib, rt._ctx)[0]) == want["n_objects"], what
+    finally:
+        rt.close()
+
+
+def test_oracle_controls_equal_the_reference():
+    """the same session on the oracle's restatement of those host methods (oracle/oracle.py)"""
+    from oracle.oracle import OracleRayTracer
+    doc = json.load(open(VECTORS))
+    rt = OracleRayTracer(600, 400)
+    rt.setCloudPermutation(np.asarray(doc["probe_perm"], np.uint8))
+    n = 0
+    for st, what in _controls_session(rt, lambda r: r.scene.camera(), doc):
+        for d, want in zip(doc["probe_dirs"], st["state"]["bgProbe"]):      # world.background on fixed rays: kind, colour and intensity
+            if want is not None:
+                eq(rt.scene.background(d), want, f"{what} background({d})"); n += 1
+        assert rt.scene.object_count() == st["state"]["n_objects"], what
+    assert n > 100
