@@ -31,7 +31,11 @@ const saved = { log: console.log, warn: console.warn };
 console.log = console.warn = () => {};
 const ref = await loadReference(path.join(REF, 'js'));
 Object.assign(console, saved);
-const cases = JSON.parse(fs.readFileSync(path.join(ROOT, 'tests', 'golden', 'reference_cases.json'), 'utf8'));
+const cases = [];
+for (const fn of ['reference_cases.json', 'reference_cases_extra.json']) {       // the 13 second-port cases + the 7 BASELINE-shaped ones
+    const p = path.join(ROOT, 'tests', 'golden', fn);
+    if (fs.existsSync(p)) cases.push(...JSON.parse(fs.readFileSync(p, 'utf8')));
+}
 const out = { generator: `baseline/make_fixtures.mjs, node ${process.version}`, cases: {} };
 for (const c of cases) {
   const r = await renderSeeded(ref, c);
