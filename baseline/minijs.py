@@ -82,6 +82,8 @@ class JSTyped(JSObject):                                   # Float32Array / Floa
             v = struct.unpack("f", struct.pack("f", v))[0] if math.isfinite(v) and abs(v) < 3.4028235677973366e38 else (v if not math.isfinite(v) else math.copysign(math.inf, v))
         elif self.kind == "u8c":                           # ToUint8Clamp: clamp to [0, 255], round half to even
             v = 0.0 if not (v > 0) else 255.0 if v >= 255 else float(round(v))
+        elif self.kind == "u8":                            # ToUint8: truncate, modulo 256
+            v = float(int(math.trunc(v)) % 256) if math.isfinite(v) else 0.0
         self.items[i] = v
 
 
@@ -195,6 +197,8 @@ def get_member(obj, key):
             if i == key: return UNDEF
         if key == "length": return float(len(obj.items))
         return obj.get(prop_key(key))
+    if isinstance(obj, JSFunction) and key == "name" and "name" not in obj.props:
+        return obj.name                                     # Function.prototype.name ("bound f" for f.bind(...))
     if isinstance(obj, JSObject):
         return obj.get(prop_key(key))
     if isinstance(obj, str):
@@ -403,7 +407,7 @@ class Parser:
                 if self.eat_kw("finally"): fin = self.block()
                 return ("try", blk, param, handler, fin)
             if v == "switch": return self.switch_stmt()
-            if v == "import": return self.import_decl()
+            if v == "import" and not self.is_p(".", 1): return self.import_decl()
             if v == "export": return self.export_decl()
         e = self.expression(); self.semi(); return ("expr", e)
     def var_decl(self):
@@ -419,7 +423,8 @@ class Parser:
             self.next(); names = []
             while not self.is_p("}"):
                 k = self.ident(); alias = self.ident() if self.eat_p(":") else k
-                names.append((k, alias)); self.eat_p(",")
+                dflt = self.assign() if self.eat_p("=") else None         # { a = 1, b: c = 2 }: used when the property is undefined
+                names.append((k, alias, dflt)); self.eat_p(",")
             self.next(); return ("objpat", names)
         if self.is_p("["):
             self.next(); names = []
@@ -658,6 +663,8 @@ class Parser:
                 params = self.params(); body = self.block()
                 return ("func", name, params, body, False, is_async)
             if v == "class": self.i -= 1; return self.class_expr()
+            if v == "import" and self.is_p(".") and self.peek(1).val == "meta":
+                self.next(); self.next(); return ("import_meta",)
             if v in CONTEXTUAL: return ("id", v)
         if k == "p":
             if v == "(":
@@ -720,6 +727,8 @@ class Interp:
     def __init__(self, module_root="."):
         self.root = module_root
         self.modules = {}
+        self._pat_defaults = {}
+        self.builtin_modules = {}                            # specifier (e.g. 'node:module') -> exports dict, provided by the host
         self.globals = Env()
         install_globals(self)
     # -- modules
@@ -731,7 +740,7 @@ class Interp:
         with open(path) as f: src = f.read()
         ast = Parser(src, os.path.basename(path)).program()
         env = Env(self.globals)
-        env.vars["%exports"] = exports; env.vars["%dir"] = os.path.dirname(path)
+        env.vars["%exports"] = exports; env.vars["%dir"] = os.path.dirname(path); env.vars["%file"] = path
         self.hoist(ast, env)
         for st in ast:
             r = self.stmt(st)(env)
@@ -775,7 +784,13 @@ class Interp:
     def bind_target(self, target, value, env):
         if target[0] == "name": env.vars[target[1]] = value
         elif target[0] == "objpat":
-            for k, alias in target[1]: env.vars[alias] = get_member(value, k)
+            for k, alias, dflt in target[1]:
+                v = get_member(value, k)
+                if v is UNDEF and dflt is not None:
+                    c = self._pat_defaults.get(id(dflt))
+                    if c is None: c = self._pat_defaults[id(dflt)] = self.expr(dflt)
+                    v = c(env)
+                env.vars[alias] = v
         else:
             for i, nm in enumerate(target[1]): env.vars[nm] = get_member(value, float(i))
     def call(self, f, this_val, args, new_target=None):
@@ -991,7 +1006,7 @@ class Interp:
         if k == "import":
             names, default, src = node[1], node[2], node[3]; interp = self
             def run(env):
-                exports = interp.load_module(os.path.join(env.get("%dir"), src))
+                exports = interp.builtin_modules[src] if src in interp.builtin_modules else interp.load_module(os.path.join(env.get("%dir"), src))
                 for kname, alias in names:
                     if kname not in exports: raise JSRuntimeError(f"module {src} does not export {kname}")
                     env.vars[alias] = exports[kname]
@@ -1040,6 +1055,8 @@ class Interp:
                     e = e.parent
                 raise JSThrow(make_error("ReferenceError", name + " is not defined"))
             return get
+        if k == "import_meta":
+            return lambda env: JSObject(OBJECT_PROTO, {"url": "file://" + str(env.get("%file"))})
         if k == "this":
             def get_this(env):
                 e = env
@@ -1694,8 +1711,12 @@ def install_globals(interp):
             arr = JSTyped(kind, len(src.items))
             for i, x in enumerate(src.items): arr.store(i, x)
             return arr
-        f = native(ctor, kind); f.props["prototype"] = TYPED_PROTO; return f
+        def typed_from(t, a):                              # %TypedArray%.from(arrayLike | iterable, mapFn)
+            return ctor(t, [arr_from(t, a)])
+        f = native(ctor, kind); f.props["prototype"] = TYPED_PROTO; f.props["from"] = native(typed_from, "from"); return f
     g["Float32Array"] = typed_ctor("f32"); g["Float64Array"] = typed_ctor("f64"); g["Uint8ClampedArray"] = typed_ctor("u8c")
+    g["Uint8Array"] = typed_ctor("u8")
+    for nm in ("Float32Array", "Float64Array", "Uint8ClampedArray", "Uint8Array"): g[nm].name = nm
     # String.prototype
     STRING_PROTO.props.update({
         "toLowerCase": native(lambda t, a: t.lower()), "toUpperCase": native(lambda t, a: t.upper()), "trim": native(lambda t, a: t.strip()),
@@ -1725,6 +1746,12 @@ def install_globals(interp):
     def set_timeout(t, a): call(a[0], UNDEF, list(a[2:])); return 0.0
     g["setTimeout"] = native(set_timeout, "setTimeout"); g["requestAnimationFrame"] = native(set_timeout, "requestAnimationFrame")
     g["clearTimeout"] = native(quiet)
+    # intervals never fire by themselves (there is no event loop): the host ticks interp.intervals when it wants time to pass
+    interp.intervals = {}
+    def set_interval(t, a):
+        k = float(len(interp.intervals) + 1 + getattr(interp, "_interval_base", 0)); interp._interval_base = k; interp.intervals[k] = a[0]; return k
+    def clear_interval(t, a): interp.intervals.pop(a[0] if a else UNDEF, None); return UNDEF
+    g["setInterval"] = native(set_interval, "setInterval"); g["clearInterval"] = native(clear_interval, "clearInterval")
     def json_parse(t, a): return py_to_js(__import__("json").loads(to_str(a[0])))
     def json_stringify(t, a): return __import__("json").dumps(js_to_py(a[0]))
     g["JSON"] = JSObject(OBJECT_PROTO, {"parse": native(json_parse, "parse"), "stringify": native(json_stringify, "stringify")})

@@ -11,9 +11,11 @@
 // putImageData is called, onProgress(fraction) fires and ends with 1.0, window.renderCancelled stops the render without
 // the final blit.  The image is written by the GPU directly into imageData.data's backing store.
 //
-// NOTE: the build image has no Node.js, so this file (pure JavaScript) has not been executed there; brt_addon.node itself is
-// loaded and driven end to end by a mock N-API host (napi/mock_node_host.c, tests/test_napi_mock.py) and produces the same
-// bytes as the Python ctypes binding (blenderraytracer_b200/) of the same C ABI.
+// NOTE: the build image has no Node.js.  This file is executed there, unmodified, by baseline/minijs.py (the interpreter that also
+// runs the reference's js/*.js) over napi/napi_host.py, a Node-API host that loads the REAL brt_addon.node: shim -> addon ->
+// libbrt, with brt_render on a worker thread, progress through a thread-safe function and the cancel poll below ticking while
+// it runs (tests/test_js_shim.py: flattening checked against the reference's live objects; image equal to the Python ctypes
+// binding's, byte for byte, on the GPU).  brt_addon.node alone is also driven by napi/mock_node_host.c (tests/test_napi_mock.py).
 //
 //   installGpuRender(RayTracer, { devices: [0, 1, 2, 3, 4, 5, 6, 7] })    // one ctx over 8 GPUs: render() is still ONE call
 import { createRequire } from 'node:module';
@@ -35,8 +37,11 @@ export function flattenWorld(world) {
   let firstTri = 0;
   for (const o of world.objects) {
     const kind = o.constructor.name;
-    const m = o.material, mk = m.constructor.name;
+    // a TriangleMesh has no `material` member: the constructor hands it to its triangles (geometry.js:231); a mesh whose every
+    // triangle was filtered out can never be hit, so any material does
     const one = { x: 1, y: 1, z: 1 };
+    const m = o.material ?? (kind === 'TriangleMesh' && o.triangles.length ? o.triangles[0].material : undefined) ?? { albedo: one, constructor: { name: 'Lambertian' } };
+    const mk = m.constructor.name;
     const color = mk === 'Emissive' ? m.color : (m.albedo ?? one);
     const param = (mk === 'Metal' || mk === 'TexturedMetal') ? m.roughness : mk === 'Dielectric' ? m.refractionIndex : mk === 'Emissive' ? m.intensity : 0;
     if (!(mk in MAT)) throw new Error(`unsupported material ${mk}`);
@@ -86,7 +91,9 @@ function backgroundOf(rt) {
   return { kind: 0, color: [0.1, 0.1, 0.1] };
 }
 
-export function installGpuRender(RayTracer, { device = 0, devices = undefined, seed = 1, preview = true } = {}) {
+// options: device | devices (one ctx over several GPUs), seed, preview (blit at every progress callback), sppBatch (samples per
+// progress step; 0 = libbrt decides)
+export function installGpuRender(RayTracer, { device = 0, devices = undefined, seed = 1, preview = true, sppBatch = 0 } = {}) {
   const origUpdateBackground = RayTracer.prototype.updateBackground;
   RayTracer.prototype.updateBackground = function (type, intensity = 1.0) {       // ray-tracer.js:568-585
     origUpdateBackground.call(this, type, intensity);
@@ -101,6 +108,7 @@ export function installGpuRender(RayTracer, { device = 0, devices = undefined, s
   const origLoad = RayTracer.prototype.loadFromJSON;
   RayTracer.prototype.loadFromJSON = function (json) {                            // ray-tracer.js:305-334
     const ok = origLoad.call(this, json);
+    if (!ok) return ok;                                              // a failed load leaves world, camera and background as they were (:329-332)
     const t = json?.background?.type;
     // deviation D1: the loader binds the solid / hdri FACTORIES (scene-loader.js:43,45 -> NaN -> black); we honour the intent
     this._brtBackground = { kind: { solid: 1, hdri: 2, procedural_sky: 3 }[t] ?? 0, color: json?.background?.color ?? [0.1, 0.1, 0.1] };
@@ -123,7 +131,7 @@ export function installGpuRender(RayTracer, { device = 0, devices = undefined, s
       seed: seed + (this._brtFrame = (this._brtFrame ?? 0) + 1),     // Math.random is unseeded: a new stream per render
       // progressive preview: before every progress callback libbrt resolves the image of the samples traced so far into
       // imageData.data, and the callback below blits it — the reference blits finished rows as it goes (:236-238)
-      preview: preview ? 1 : 0,
+      preview: preview ? 1 : 0, sppBatch,
     });
     const poll = setInterval(() => { if (globalThis.window?.renderCancelled) addon.cancel(ctx); }, 50);   // :190,:256
     try {

@@ -71,6 +71,12 @@ CASES = [
     # typed arrays: Float32Array rounds on store, Uint8ClampedArray clamps and rounds half to even
     ("const f = new Float32Array(2); f[0] = 0.1; f[1] = 16777217; let out = [f[0], f[1], f.length];", [0.10000000149011612, 16777216, 2]),
     ("const u = new Uint8ClampedArray(6); u[0] = -5; u[1] = 300; u[2] = 1.5; u[3] = 2.5; u[4] = 254.5; u[5] = NaN; let out = [u[0], u[1], u[2], u[3], u[4], u[5]];", [0, 255, 2, 2, 254, 0]),
+    # what napi/raytracer_gpu.mjs needs beyond the reference's subset
+    ("function f({ a = 1, b: c = 2, d } = {}) { return [a, c, d]; } let out = [f(), f({ a: 5, b: 6, d: 7 }), f({ a: undefined, b: null })];", [[1, 2, None], [5, 6, 7], [1, None, None]]),
+    ("const u = Uint8Array.from([1, 255, 256, -1, 3.9]); const f = new Float64Array([0.1, 2]); let out = [u[0], u[1], u[2], u[3], u[4], u.length, f[0], Uint8Array.name];", [1, 255, 0, 255, 3, 5, 0.1, "Uint8Array"]),
+    ("class K {} function g() {} const o = { m() {} }; let out = [new K().constructor.name, g.name, g.bind(null).name, (() => 1).name, o.m.name];", ["K", "g", "bound g", "", "m"]),
+    ("let n = 0; const id = setInterval(() => { n++; }, 50); clearInterval(id); let out = [typeof id, n];", ["number", 0]),     # intervals are ticked by the host only
+    ("const o = { solid: 1, hdri: 2 }; let out = [o['solid'] ?? 0, o['x'] ?? 0, { a: 1 }['a'], Array.from({ length: 3 }, (_, i) => i * 2)];", [1, 0, 1, [0, 2, 4]]),
     # async / await over immediately resolved promises (the reference yields with setTimeout between rows)
     ("let out = 0; async function r() { await new Promise(res => setTimeout(res, 1)); out = 7; return 3; } r();", 7.0),
 ]
@@ -100,6 +106,17 @@ def test_modules_import_export(tmp_path):
     ex = interp.load_module(str(tmp_path / "b.js"))
     assert interp.call(ex["f"], J.UNDEF, []) == 42.0
     assert set(ex) == {"Q", "f"}
+
+
+def test_host_modules_and_import_meta(tmp_path):
+    """`import { createRequire } from 'node:module'` resolves to what the embedding host registered; import.meta.url names the file"""
+    (tmp_path / "m.mjs").write_text("import { createRequire } from 'node:module';\nconst require = createRequire(import.meta.url);\n"
+                                    "export const got = require('./x.node');\nexport const url = import.meta.url;\n")
+    interp = J.Interp()
+    seen = []
+    interp.builtin_modules["node:module"] = {"createRequire": J.native(lambda t, a: (seen.append(a[0]), J.native(lambda t2, a2: "addon:" + a2[0]))[1])}
+    ex = interp.load_module(str(tmp_path / "m.mjs"))
+    assert ex["got"] == "addon:./x.node" and ex["url"] == "file://" + str(tmp_path / "m.mjs") and seen == [ex["url"]]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine")
