@@ -1583,7 +1583,7 @@ def install_globals(interp):
     })
     g["Math"] = Math
     g["Infinity"] = math.inf; g["NaN"] = math.nan; g["undefined"] = UNDEF
-    g["globalThis"] = JSObject(OBJECT_PROTO)
+    g["globalThis"] = JSObject(OBJECT_PROTO, g)           # the global object: its properties ARE the global bindings
     quiet = lambda t, a: UNDEF
     interp.console_lines = []
     def log(t, a): interp.console_lines.append(" ".join(to_str(x) for x in a)); return UNDEF

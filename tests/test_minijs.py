@@ -77,6 +77,7 @@ CASES = [
     ("class K {} function g() {} const o = { m() {} }; let out = [new K().constructor.name, g.name, g.bind(null).name, (() => 1).name, o.m.name];", ["K", "g", "bound g", "", "m"]),
     ("let n = 0; const id = setInterval(() => { n++; }, 50); clearInterval(id); let out = [typeof id, n];", ["number", 0]),     # intervals are ticked by the host only
     ("const o = { solid: 1, hdri: 2 }; let out = [o['solid'] ?? 0, o['x'] ?? 0, { a: 1 }['a'], Array.from({ length: 3 }, (_, i) => i * 2)];", [1, 0, 1, [0, 2, 4]]),
+    ("globalThis.zz = 5; let out = [zz, globalThis.Math === Math, globalThis.nope?.x, typeof globalThis.setInterval];", [5, True, None, "function"]),
     # async / await over immediately resolved promises (the reference yields with setTimeout between rows)
     ("let out = 0; async function r() { await new Promise(res => setTimeout(res, 1)); out = 7; return 3; } r();", 7.0),
 ]
