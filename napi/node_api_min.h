@@ -1,7 +1,8 @@
 /* Minimal declaration of the stable Node-API (N-API v4) surface used by brt_addon.c.
  *
  * The build image has no Node.js (no `node`, no node_api.h), so the addon is compiled against these prototypes; it is
- * loaded and driven here by napi/mock_node_host.c, which implements them (tests/test_napi_mock.py).  With a Node toolchain
+ * loaded and driven here by napi/mock_node_host.c, which implements them (tests/test_napi_mock.py), and by napi/napi_host.py,
+ * the N-API host under which the JS shim itself is executed (tests/test_js_shim.py).  With a Node toolchain
  * present, brt_addon.c includes the real <node_api.h> instead (see the __has_include test there) — the declarations below
  * restate that header's C ABI for the functions we call and nothing else. */
 #ifndef BRT_NODE_API_MIN_H
