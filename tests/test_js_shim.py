@@ -220,3 +220,48 @@ def test_shim_cancel_through_window_render_cancelled(addon):
     interp.call(rt.get("render"), rt, [J.native(on_progress)])
     assert progress[-1] == 1.0 and len(blits) == 1
     host.finalize_external(rt.get("_brt")); py.close()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="no reference checkout on this machine")
+def test_shim_flattens_the_reference_textured_materials(addon):
+    """TexturedLambertian / TexturedMetal over Checker / Noise / Marble / Wood / SolidColor textures built by the reference's own
+    constructors (js/materials.js:99-126, js/textures.js): the texture table that reaches libbrt has the kind, colours, scale and
+    the texture's own Perlin table (noise.p) of each live object, and the material rows point at it."""
+    import make_texture_fixtures_minijs as T
+    interp, host, shim = node_like(addon)
+    js = "/root/reference/js"
+    RayTracer = interp.load_module(js + "/ray-tracer.js")["RayTracer"]
+    Vec3 = interp.load_module(js + "/math.js")["Vec3"]
+    tex_ex, mat_ex = interp.load_module(js + "/textures.js"), interp.load_module(js + "/materials.js")
+    interp.call(shim["installGpuRender"], J.UNDEF, [RayTracer, J.py_to_js({"device": -1})])
+    rt = interp.construct(RayTracer, [fake_canvas(64, 48, [])])
+    assert J.truthy(interp.call(rt.get("loadFromJSON"), rt, [J.py_to_js(json.load(open(os.path.join(GOLDEN, "sample_scene.json"))))]))
+    objs = rt.get("world").get("objects").items
+    by_name = {t["name"]: t for t in T.TEXTURES}
+    assign = {0: "checker10", 1: "marble", 2: "wood", 3: "noise4", 4: "solid"}
+    used = {}
+    for i, name in assign.items():
+        if i >= len(objs): continue
+        m = objs[i].get("material"); cls = m.proto.get("constructor").name
+        tex = T.make_texture(interp, tex_ex, Vec3, by_name[name])
+        if cls == "Lambertian": objs[i].set("material", interp.construct(mat_ex["TexturedLambertian"], [tex])); used[i] = (name, 0, 0.0)
+        elif cls == "Metal": objs[i].set("material", interp.construct(mat_ex["TexturedMetal"], [tex, m.get("roughness")])); used[i] = (name, 1, m.get("roughness"))
+    assert len(used) >= 3
+    interp.globals.vars["window"].set("renderCancelled", False)
+    with pytest.raises(J.JSThrow):
+        interp.call(rt.get("render"), rt, [J.native(lambda t, a: J.UNDEF)])
+    assert not host.log, host.log
+    d = L.brt_scene_desc()
+    assert brt.load().brt_scene_get_flat(ctx_of(rt), C.byref(d)) == L.BRT_OK
+    assert d.n_textures == len(used) and d.n_objects == len(objs)
+    for i, (name, mat_type, rough) in used.items():
+        t, mat = by_name[name], d.materials[d.objects[i].material]
+        assert mat.type == mat_type and mat.param == rough and 1 <= mat.texture <= d.n_textures, (i, name)
+        tx = d.textures[mat.texture - 1]
+        assert tx.kind == L.TEX[t["kind"]] and tx.scale == t["scale"], (i, name)
+        assert tuple(tx.odd) == tuple(map(float, t["odd"])), (i, name)
+        if t["kind"] == "checker": assert tuple(tx.even) == tuple(map(float, t["even"]))
+        if t["perm_seed"] is not None: assert list(tx.perm) == T.perm_of(t["perm_seed"]), (i, name)
+    for i in range(d.n_objects):
+        if i not in used: assert d.materials[d.objects[i].material].texture == 0
+    host.finalize_external(rt.get("_brt"))
