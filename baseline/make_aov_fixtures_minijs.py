@@ -39,7 +39,46 @@ def cases():
         dict(name="c3_random_spheres", W=48, H=27, scene=gen_scenes.random_spheres(grid=3)),
         dict(name="c4_cornell", W=48, H=27, scene=gen_scenes.cornell("hdri")),
         dict(name="c5_terrain", W=48, H=27, scene=gen_scenes.terrain(quads=10, extent=200.0)),
+        dict(name="axis_parallel_rays_and_zero_over_zero", W=45, H=31, scene=axis_parallel_scene()),
+        dict(name="orthographic_from_inside", W=40, H=30, scene=inside_scene()),
     ]
+
+
+def axis_parallel_scene():
+    """An axis-aligned camera with odd W and H: the centre column has D.x = 0 and the centre row D.y = 0 EXACTLY, so Box.hit
+    (geometry.js:85-112) divides by zero — (bound - O) / 0 = +-Infinity, and 0 / 0 = NaN where a box face lies exactly at the ray
+    origin's coordinate (boxes 0 and 1 below) — and Math.max / Math.min propagate the NaN.  Spheres, triangles, a mesh and a plane
+    straddle the same axes."""
+    lam = lambda c: dict(type="lambertian", color=c)
+    objs = [
+        dict(type="box", min=[0.5, 0.2, -1.0], max=[1.5, 1.4, 0.0], material=lam([0.8, 0.2, 0.2])),      # min.x = O.x: 0/0 on the centre column
+        dict(type="box", min=[-1.5, 1.0, -2.0], max=[-0.2, 1.8, -1.0], material=lam([0.2, 0.8, 0.2])),   # min.y = O.y: 0/0 on the centre row
+        dict(type="box", min=[-0.4, -0.5, -3.0], max=[0.4, 0.6, -2.5], material=lam([0.2, 0.2, 0.8])),   # straddles x = 0.5? no: left of it
+        dict(type="box", min=[0.1, 0.6, -4.0], max=[0.9, 1.6, -3.5], material=lam([0.8, 0.8, 0.2])),     # straddles both centre lines
+        dict(type="sphere", center=[0.5, 1.0, -6.0], radius=1.2, material=lam([0.5, 0.5, 0.5])),
+        dict(type="sphere", center=[-1.0, 0.2, 1.0], radius=0.6, material=dict(type="metal", color=[0.9, 0.9, 0.9], roughness=0.1)),
+        dict(type="sphere", center=[2.0, 1.9, 0.5], radius=0.7, material=dict(type="dielectric", ior=1.5)),
+        dict(type="triangle", v0=[0.5, 1.0, -4.5], v1=[2.6, 1.0, -4.5], v2=[0.5, 3.2, -4.5], material=lam([0.9, 0.4, 0.1])),   # edges ON the centre lines
+        dict(type="mesh", vertices=[[-3, -0.5, -4.6], [0.5, -0.5, -4.6], [0.5, 1.0, -4.6], [-3, 1.0, -4.6]], indices=[0, 1, 2, 0, 2, 3], material=lam([0.3, 0.6, 0.9])),
+        dict(type="plane", point=[0, -0.5, 0], normal=[0, 1, 0], material=lam([0.4, 0.4, 0.4])),
+        dict(type="plane", point=[0, 0, -9], normal=[0, 0, 1], material=lam([0.6, 0.5, 0.4])),
+    ]
+    return dict(objects=objs, lights=[], camera=dict(position=[0.5, 1.0, 5.0], lookAt=[0.5, 1.0, 0.0], up=[0, 1, 0], fov=50, aspect=45 / 31, aperture=0.0, focusDist=5.0),
+                background=dict(type="gradient", intensity=1.0))
+
+
+def inside_scene():
+    """orthographic camera placed INSIDE a large glass sphere and a box: back-face hits (frontFace false, flipped normals), the second
+    sphere root (geometry.js:22-26) and Box.hit's `t0 > tMin ? t0 : t1` exit-face choice (:109)"""
+    objs = [
+        dict(type="sphere", center=[0, 0, 0], radius=3.0, material=dict(type="dielectric", ior=1.5)),
+        dict(type="box", min=[-2.5, -2.0, -6.0], max=[2.5, 2.0, 2.0], material=dict(type="lambertian", color=[0.7, 0.7, 0.7])),
+        dict(type="sphere", center=[0.8, 0.3, -1.5], radius=-0.5, material=dict(type="dielectric", ior=1.5)),                      # negative radius
+        dict(type="triangle", v0=[-1, -1, -2.2], v1=[1, -1, -2.2], v2=[0, 1, -2.2], material=dict(type="metal", color=[0.8, 0.8, 0.8], roughness=0.0)),
+    ]
+    return dict(objects=objs, lights=[], camera=dict(position=[0.2, 0.1, 1.0], lookAt=[0.2, 0.1, -1.0], up=[0, 1, 0], fov=60, aspect=40 / 30, aperture=0.0,
+                                                      focusDist=2.0, type="orthographic"),
+                background=dict(type="solid", color=[0.2, 0.2, 0.2], intensity=1.0))
 
 
 def main():
