@@ -655,6 +655,8 @@ __device__ __forceinline__ D3 cross(D3 a, D3 b) {
     return d3(__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)), __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
               __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
 }
+__device__ __forceinline__ double js_max(double a, double b) { return (a != a || b != b) ? __dadd_rn(a, b) : (a > b ? a : b); }   // Math.max: NaN if either is
+__device__ __forceinline__ double js_min(double a, double b) { return (a != a || b != b) ? __dadd_rn(a, b) : (a < b ? a : b); }
 __device__ __forceinline__ D3 normalize0(D3 a) { double l = sqrt(dot(a, a)); return l > 0 ? a / l : d3(0, 0, 0); }
 __device__ __forceinline__ D3 ldd3(const double* p) { return d3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 __device__ __forceinline__ float3 tof3(D3 a) { return f3((float)a.x, (float)a.y, (float)a.z); }
@@ -695,11 +697,14 @@ static __device__ __noinline__ bool refine_primary(const DevScene& sc, uint32_t 
         double y0 = __ddiv_rn(__dsub_rn(mn.y, O.y), D.y), y1 = __ddiv_rn(__dsub_rn(mx.y, O.y), D.y);
         if (y0 > y1) { double w = y0; y0 = y1; y1 = w; }
         if (t0 > y1 || y0 > t1) return false;
-        t0 = fmax(t0, y0); t1 = fmin(t1, y1);
+        // Math.max / Math.min PROPAGATE NaN (fmax / fmin drop it): a ray parallel to a slab whose face passes through the ray
+        // origin gives 0 / 0 = NaN, and the reference then leaves through `t0 > tMin ? t0 : t1` with t1 (pinned against the
+        // reference's own Box.hit: tests/golden/reference_aov_vectors.json, case axis_parallel_rays_and_zero_over_zero)
+        t0 = js_max(t0, y0); t1 = js_min(t1, y1);
         double z0 = __ddiv_rn(__dsub_rn(mn.z, O.z), D.z), z1 = __ddiv_rn(__dsub_rn(mx.z, O.z), D.z);
         if (z0 > z1) { double w = z0; z0 = z1; z1 = w; }
         if (t0 > z1 || z0 > t1) return false;
-        t0 = fmax(t0, z0); t1 = fmin(t1, z1);
+        t0 = js_max(t0, z0); t1 = js_min(t1, z1);
         t = t0 > tMin ? t0 : t1;
         if (!(t >= tMin)) return false;
         D3 P = O + D * t;
