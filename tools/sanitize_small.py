@@ -24,10 +24,22 @@ for name, sc in scenes.items():
                 rt.directLighting = (name == "mesh" and sampler == "reference")
                 img = rt.render(want_linear=True)
                 assert img.shape == (27, 45, 4)
+    rt.integrator, rt.accel, rt.sampler, rt.directLighting = "megakernel", "bvh", "fast", False
+    for width in (4, 8, 2, 0):                   # the wide collapses of the hierarchy and back
+        rt.bvhWidth = width
+        rt.render()
     rt.countTests = True
     rt.render()
     rt.countTests = False
     rt.primaryAOV(32); rt.primaryAOV(64)
     rt.evalBackground(np.random.default_rng(0).normal(size=(100, 3)))
     print(name, "ok", flush=True)
+# a mesh large enough for the GPU LBVH + the host SAH candidate + the wide level builder to run with many levels
+rt = brt.RayTracer(64, 36, seed=3)
+assert rt.loadFromJSON(gen_scenes.terrain(quads=40))
+rt.updateRenderSettings(dict(samples=2, maxBounces=3))
+for width in (2, 4, 8):
+    rt.bvhWidth = width
+    rt.render()
+print("terrain40 ok", flush=True)
 print("SANITIZE_SMALL_DONE")
