@@ -457,6 +457,9 @@ __device__ __forceinline__ bool node_visit_ch(const float4* __restrict__ nodes, 
     return h0 | h1;
 }
 
+#ifndef BRT_LEAF_WAIT_K
+#define BRT_LEAF_WAIT_K 0
+#endif
 // Blocking traversal: runs one ray to completion.  HYBRID = false: the whole stack lives in shared memory (the launcher
 // sized it from the tree depth: depth + 1 entries per thread) and the loop carries no local-memory path at all;
 // HYBRID = true (trees deeper than SMEM_ONLY_MAX_DEPTH): SMEM_STACK entries in shared memory, the rest in a local array.
@@ -493,6 +496,19 @@ __device__ __forceinline__ Hit trace_bvh(const DevScene& sc, float3 O, float3 D,
             }
         }
         bool pop = true;
+#if BRT_LEAF_WAIT_K > 0
+        // EXPERIMENT (rejected by measurement, profiles/r02c_leaf_wait_rejected.md; off by default): a lane that holds a leaf waits
+        // until at least BRT_LEAF_WAIT_K lanes of the warp hold one (or no lane has node work left), so that the leaf block is
+        // issued for fuller warps.  No speculation: the waiting lane does nothing, its ray's state is untouched.
+        bool hold = false;
+        {
+            const unsigned actW = __activemask();
+            const unsigned leafW = __ballot_sync(actW, (cur & LEAF_BIT) != 0u);
+            hold = (cur & LEAF_BIT) != 0u && __popc(leafW) < BRT_LEAF_WAIT_K && leafW != actW;
+        }
+        if (hold) pop = false;
+        else
+#endif
         if (cur & LEAF_BIT) {
             test_prim<COUNT, SHADOW, PRIMS>(sc, cur & ~LEAF_BIT, O, D, tMin, self, best, cnt);
             if (SHADOW && best.pid != PID_NONE) break;
