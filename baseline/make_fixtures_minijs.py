@@ -24,6 +24,7 @@ here and from V8's fdlibm port there (last-ulp differences possible); + - * / an
 """
 import argparse
 import json
+import math
 import os
 import sys
 import time
@@ -132,11 +133,55 @@ def render_seeded(interp, RayTracer, Vec3, c):
     math_obj.set("random", J.native(lambda t, a: stream.next()))
     interp.globals.vars["window"].set("renderCancelled", False)
     try:
+        if c.get("rect"):
+            return render_rect(interp, rt, Vec3, c, linear, fdat)
         interp.call(rt.get("render"), rt, [J.native(lambda t, a: J.UNDEF)])
     finally:
         math_obj.set("random", saved)
     data = rt.get("imageData").get("data").items
     return {"rgba": [int(v) for v in data], "linear": linear, "float": fdat}
+
+
+def render_rect(interp, rt, Vec3, c, linear, fdat):
+    """A window of a frame too large to run whole under the interpreter (the BASELINE configs at 1920x1080): the body of the
+    reference's pixel loop (js/ray-tracer.js:199-228) for the pixels of c["rect"] = [x0, y0, x1, y1] (row 0 = top), every step a call
+    of the reference's OWN method — getAntiAliasSample, camera.getRay, rayColor, Vec3.add / div, toneMap, gammaCorrect — and the
+    Math.floor(c * 255) store through a Uint8ClampedArray (:226-228).  Returns the crop only."""
+    x0, y0, x1, y1 = c["rect"]
+    W, H = c["W"], c["H"]
+    cam = rt.get("camera")
+    n = rt.get("samples") if rt.get("antiAliasing") != "none" else 1.0                # :201
+    out_lin, out_f, out_rgba = [], [], J.JSTyped("u8c", (x1 - x0) * (y1 - y0) * 4)
+    k = 0
+    for y in range(y0, y1):
+        j = H - 1 - y
+        for i in range(x0, x1):
+            color = interp.construct(Vec3, [0.0, 0.0, 0.0])
+            for smp in range(int(n)):
+                sample = method(interp, rt, "getAntiAliasSample", float(i), float(j), float(smp))
+                ray = method(interp, cam, "getRay", sample.get("u"), sample.get("v"))
+                color = method(interp, color, "add", method(interp, rt, "rayColor", ray, rt.get("maxBounces")))
+            color = method(interp, color, "div", n)
+            p = ((H - 1 - j) * W + i) * 3
+            col = method(interp, rt, "toneMap", color)               # the wrappers record linear[] / fdat[] at the full-frame index
+            col = method(interp, rt, "gammaCorrect", col)
+            out_lin += linear[p:p + 3]; out_f += fdat[p:p + 3]
+            for ch, key in enumerate(("x", "y", "z")):
+                out_rgba.store(k + ch, math.floor(col.get(key) * 255) if col.get(key) == col.get(key) else col.get(key))
+            out_rgba.store(k + 3, 255.0)
+            k += 4
+    return {"rgba": [int(v) for v in out_rgba.items], "linear": out_lin, "float": out_f}
+
+
+def expand_case(c):
+    """a case may name its scene by generator (tools/gen_scenes.py, deterministic) instead of carrying it: {"gen": [name, kwargs]}"""
+    if "gen" in c and "scene" not in c:
+        sys.path.insert(0, ROOT)
+        from tools import gen_scenes
+        import io, contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            c = dict(c, scene=getattr(gen_scenes, c["gen"][0])(**c["gen"][1]))
+    return c
 
 
 def main():
@@ -150,7 +195,7 @@ def main():
         sys.exit(f"{js_dir}: no reference checkout (pass --ref)")
     sys.setrecursionlimit(20000)
     cases = []
-    for fn in ("reference_cases.json", "reference_cases_extra.json"):      # the 13 second-port cases + the BASELINE-shaped extras
+    for fn in ("reference_cases.json", "reference_cases_extra.json", "reference_cases_fullsize.json"):      # 13 second-port cases, BASELINE-shaped extras, full-size windows
         path = os.path.join(ROOT, "tests", "golden", fn)
         if os.path.exists(path):
             cases += json.load(open(path))
@@ -162,6 +207,7 @@ def main():
     for c in cases:
         if only and c["name"] not in only:
             continue
+        c = expand_case(c)
         t0 = time.time()
         interp, RayTracer, Vec3 = load_reference(js_dir)                 # a fresh module graph per case, as a page load
         r = render_seeded(interp, RayTracer, Vec3, c)

@@ -694,6 +694,38 @@ def test_gpu_tracks_the_reference_vectors_sample_for_sample(brt):
     assert np.mean([v[1] for v in worst.values()]) >= 0.999, worst
 
 
+def test_gpu_full_size_frames_track_the_reference_windows(brt):
+    """BASELINE-size frames against the reference itself: the GPU renders the whole 1920x1080 frame of C3 (486 objects, thin lens,
+    depth 10) and C4 (Cornell under the procedural sky, depth 16, ACES) with sampler = reference; inside the windows for which the
+    reference's own pixel loop was executed (tests/golden/reference_cases_fullsize.json -> reference_vectors.json) the pixels must be
+    the reference's: same paths in fp32 instead of float64."""
+    from tools import gen_scenes
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    doc = json.load(open(os.path.join(G, "reference_vectors.json")))
+    cases = json.load(open(os.path.join(G, "reference_cases_fullsize.json")))
+    assert len(cases) >= 2
+    for c in cases:
+        W, H, want = c["W"], c["H"], doc["cases"][c["name"]]
+        assert (W, H) == (1920, 1080)
+        x0, y0, x1, y1 = c["rect"]
+        rt = brt.RayTracer(W, H, seed=c["seed"])
+        assert rt.loadFromJSON(getattr(gen_scenes, c["gen"][0])(**c["gen"][1]))
+        rt.setCloudPermutation(np.asarray(c["perm"], np.uint8))
+        rt.updateRenderSettings(dict(samples=c["spp"], maxBounces=c["depth"], antiAliasing=c["aa"], toneMapping=c["tonemap"], exposure=c["exposure"],
+                                     gamma=c["gamma"], denoising=c["denoise"], denoiseStrength=c["strength"]))
+        rt.sampler = "reference"
+        img = rt.render(want_linear=True)
+        lin = np.asarray(want["linear"], np.float64).reshape(y1 - y0, x1 - x0, 3)
+        rgba = np.asarray(want["rgba"], np.uint8).reshape(y1 - y0, x1 - x0, 4)
+        err = np.abs(rt.linearMean[y0:y1, x0:x1, :3] - lin)
+        d = np.abs(img[y0:y1, x0:x1, :3].astype(int) - rgba[..., :3].astype(int)).max(axis=-1)
+        print(f"[full-size window] {c['name']}: median |linear err| {np.median(err):.2e}, max {err.max():.2e}, RGBA8 identical on {(d == 0).mean():.4f} of {d.size} pixels")
+        assert lin.std() > 0.01                                         # the window shows structure, not a flat background
+        assert np.median(err) <= 1e-6, (c["name"], float(np.median(err)))
+        assert (d == 0).mean() >= 0.98 and (d <= 2).mean() >= 0.99, (c["name"], float((d == 0).mean()))
+        rt.close()
+
+
 def test_gpu_primary_visibility_equals_the_reference(brt):
     """North-star gate "primary-hit object IDs bit-exact" against the reference ITSELF: camera.getRay + World.hit of the unmodified
     js/*.js at every pixel centre (tests/golden/reference_aov_vectors.json, baseline/make_aov_fixtures_minijs.py) vs the float64

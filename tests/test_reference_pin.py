@@ -12,7 +12,9 @@ imports) computes for 20 cases with Math.random replaced by the oracle's Philox 
 
 The cases: the 13 of the second-port cross-check (both fixtures, the four presets, the four backgrounds, all AA / tone-map modes,
 denoise, the orthographic camera) + 7 shaped like the BASELINE configs (fixtures at depth 10, Cornell at depth 16 with ACES and
-denoise, thin-lens random spheres, a terrain mesh under the procedural sky, the duplicate / coplanar tie scene)."""
+denoise, thin-lens random spheres, a terrain mesh under the procedural sky, the duplicate / coplanar tie scene) + 2 windows of
+BASELINE-size frames (reference_cases_fullsize.json: 20x12 pixels of the 1920x1080 C3 and C4 frames, the reference's pixel-loop
+body run through its own methods)."""
 import json
 import os
 
@@ -25,10 +27,23 @@ from oracle.oracle import OracleRayTracer
 VECTORS = os.path.join(GOLDEN, "reference_vectors.json")
 CASES = os.path.join(GOLDEN, "reference_cases.json")
 EXTRA = os.path.join(GOLDEN, "reference_cases_extra.json")
+FULLSIZE = os.path.join(GOLDEN, "reference_cases_fullsize.json")
+
+
+def expand(c):
+    """a case may name its scene by generator (tools/gen_scenes.py, deterministic) instead of carrying it"""
+    if "gen" in c and "scene" not in c:
+        from tools import gen_scenes
+        c = dict(c, scene=getattr(gen_scenes, c["gen"][0])(**c["gen"][1]))
+    return c
 
 
 def all_cases():
-    return json.load(open(CASES)) + (json.load(open(EXTRA)) if os.path.exists(EXTRA) else [])
+    out = json.load(open(CASES))
+    for fn in (EXTRA, FULLSIZE):
+        if os.path.exists(fn):
+            out += [expand(c) for c in json.load(open(fn))]
+    return out
 
 
 def oracle_render(c):
@@ -41,7 +56,7 @@ def oracle_render(c):
     rt.setCloudPermutation(np.asarray(c["perm"], np.uint8))
     rt.updateRenderSettings(dict(samples=c["spp"], maxBounces=c["depth"], antiAliasing=c["aa"], toneMapping=c["tonemap"],
                                  exposure=c["exposure"], gamma=c["gamma"], denoising=c["denoise"], denoiseStrength=c["strength"]))
-    img = rt.render()
+    img = rt.render(rect=tuple(c["rect"])) if c.get("rect") else rt.render()
     return rt, img
 
 
@@ -64,22 +79,26 @@ def test_oracle_matches_the_reference_itself():
     doc = json.load(open(VECTORS))
     ref, exact = doc["cases"], "minijs" in doc.get("generator", "")
     cases = all_cases()
-    assert len(cases) >= 20 and all(c["name"] in ref for c in cases), sorted(set(c["name"] for c in cases) - set(ref))
+    assert len(cases) >= 22 and all(c["name"] in ref for c in cases), sorted(set(c["name"] for c in cases) - set(ref))
     for c in cases:
         name, W, H = c["name"], c["W"], c["H"]
         want = ref[name]
         rt, img = oracle_render(c)
-        lin = np.asarray(want["linear"], np.float64).reshape(H, W, 3)
-        fdat = np.asarray(want["float"], np.float64).reshape(H, W, 3)
-        rgba = np.asarray(want["rgba"], np.uint8).reshape(H, W, 4)
+        # a window of a BASELINE-size frame (reference_cases_fullsize.json): the vectors hold the window only
+        x0, y0, x1, y1 = c.get("rect") or (0, 0, W, H)
+        h, w = y1 - y0, x1 - x0
+        lin = np.asarray(want["linear"], np.float64).reshape(h, w, 3)
+        fdat = np.asarray(want["float"], np.float64).reshape(h, w, 3)
+        rgba = np.asarray(want["rgba"], np.uint8).reshape(h, w, 4)
+        got_lin, got_f, img = rt.linear[y0:y1, x0:x1, :3], rt.floatData[y0:y1, x0:x1, :3], img[y0:y1, x0:x1]
         assert np.isfinite(lin).all() and lin.max() > 0, name
         if exact:
             # same arithmetic, same libm: the oracle must reproduce the reference's own numbers bit for bit
-            assert np.array_equal(rt.linear[..., :3], lin), (name, int((rt.linear[..., :3] != lin).sum()))
-            assert np.array_equal(rt.floatData[..., :3], fdat.astype(np.float32)), name      # floatData is a Float32Array (ray-tracer.js:186)
+            assert np.array_equal(got_lin, lin), (name, int((got_lin != lin).sum()))
+            assert np.array_equal(got_f, fdat.astype(np.float32)), name      # floatData is a Float32Array (ray-tracer.js:186)
             assert np.array_equal(img, rgba), (name, int((img != rgba).sum()))
         else:
-            np.testing.assert_allclose(rt.linear[..., :3], lin, rtol=1e-12, atol=1e-15, err_msg=name)
+            np.testing.assert_allclose(got_lin, lin, rtol=1e-12, atol=1e-15, err_msg=name)
             assert np.abs(img.astype(int) - rgba.astype(int)).max() <= 1, name
         assert (rgba[..., 3] == 255).all(), name
 
