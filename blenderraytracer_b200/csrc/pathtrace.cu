@@ -4,6 +4,9 @@
 // Replaces the three nested loops of RayTracer.render (ray-tracer.js:189-206) and the recursion of
 // rayColor (ray-tracer.js:102-123) — written iteratively: sum += beta ⊙ E; beta ⊙= attenuation.
 #include "pathtrace_common.cuh"
+#ifndef BRT_STEAL
+#define BRT_STEAL 0
+#endif
 
 namespace brt {
 
@@ -27,9 +30,9 @@ template <int SAMPLER, bool USE_BVH, bool COUNT, bool DIRECT, bool HYBRID, int P
 __global__ void __launch_bounds__(MEGA_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_mega(const __grid_constant__ PTParams p) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int col = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int row = blockIdx.y * (MEGA_BLOCK / 16) + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = col < p.W && row < p.rowEnd && row >= p.rowBegin;
+    const int col0 = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int row0 = blockIdx.y * (MEGA_BLOCK / 16) + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = col0 < p.W && row0 < p.rowEnd && row0 >= p.rowBegin;
     const DevScene& sc = p.sc;
     // float64 primary rays + float64 evaluation of the primary hit: always with the sequential (reference) sampler — the mode
     // that is compared sample for sample with the float64 oracle — and in the AOV kernel; the fast sampler is fp32 throughout
@@ -39,14 +42,36 @@ __global__ void __launch_bounds__(MEGA_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_me
     constexpr bool PRECISE = SAMPLER == 1;
 #endif
     constexpr bool CH = BRT_NODE_CH && SAMPLER == 0;                      // fast sampler: centre / half-extent node copy (node_visit_ch)
+    // STEAL (fast sampler): the samples of a warp's 8x4 tile are ONE pool of work items (pixel slot, sample index) that the 32 lanes
+    // draw from through a shared-memory counter, instead of lane L owning pixel L's samples.  Path lengths are random, so with the
+    // static binding the lanes of a warp finish their pixels at different times and wait drained (6.7 % of the BVH-loop lane
+    // slots at 256 spp per launch, 22 % at 16: profiles/r02_lane_attribution_balanced_vs_static.md); drawing from a pool, they all
+    // finish within one path of each other.  A sample's value depends only on (pixel, sample index) — the Philox counter — never on
+    // the lane that traced it, and the per-pixel sums are kept in fixed point (2^-20, 16-bit limbs) in shared memory, so the result does
+    // not depend on which lane added what when: bit-reproducible, and identical for every hierarchy / integrator variant.
+    constexpr bool STEAL = BRT_STEAL && SAMPLER == 0;
+    __shared__ unsigned int tileSum[STEAL ? MEGA_BLOCK / 32 : 1][STEAL ? 32 : 1][6];
+    __shared__ unsigned int tileNext[STEAL ? MEGA_BLOCK / 32 : 1], tileNaN[STEAL ? MEGA_BLOCK / 32 : 1], tileInf[STEAL ? MEGA_BLOCK / 32 : 1];
+    const unsigned insideMask = STEAL ? __ballot_sync(0xffffffffu, inside) : 0u;
+    if (STEAL) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) tileSum[warp][lane][k] = 0u;
+        if (lane == 0) { tileNext[warp] = 0u; tileNaN[warp] = 0u; tileInf[warp] = 0u; }
+        __syncwarp();
+    }
     Counters cnt = {};
-    if (inside) {
-        const int jUp = p.H - 1 - row;
-        const uint32_t pix = (uint32_t)(row * p.W + col);
+    if (STEAL ? insideMask != 0u : inside) {
+        int col = col0, row = row0;                                           // STEAL: the pixel of the path in flight, not the lane's own
+        int jUp = p.H - 1 - row;
+        uint32_t pix = (uint32_t)(row * p.W + col);
         const int per = (p.sCount + gridDim.z - 1) / gridDim.z;
         int s = p.sBegin + blockIdx.z * per;
         const int sEnd = min(p.sBegin + p.sCount, s + per);
         const int nMine = max(0, sEnd - s);
+        const int tileCnt = __popc(insideMask);
+        uint32_t tileTotal = (uint32_t)tileCnt * (uint32_t)nMine;            // work items of this warp's tile
+        uint32_t slot = (uint32_t)lane;                                       // pixel slot (0..31 within the tile) of the path in flight
+        bool have = false;
         float3 sum = f3(0.f, 0.f, 0.f), beta = f3(1.f, 1.f, 1.f), O = f3(0, 0, 0), D = f3(0, 0, 1);
         uint32_t self = PID_NONE, cs = 0;
         int depth = 0;
@@ -55,15 +80,42 @@ __global__ void __launch_bounds__(MEGA_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_me
         uint32_t hitPid = PID_NONE;
         RngSeq rng;
         uint32_t* sstack = smem + threadIdx.x;
-        if (p.maxDepth <= 0) s = sEnd;                                        // rayColor(depth <= 0) is black (ray-tracer.js:103): only alpha moves
+        if (p.maxDepth <= 0) { s = sEnd; tileTotal = 0u; }                    // rayColor(depth <= 0) is black (ray-tracer.js:103): only alpha moves
         // One iteration = [draw] -> [start a path: camera ray | continue one: scatter at the previous hit] -> trace -> [miss:
         // background | hit: surface + emission].  The lanes that start a path and the lanes that continue one draw their
         // Philox block in the SAME call (counter block 0 / block depth): one full-warp instance of the generator instead of
         // two half-empty ones.
         for (;;) {
             if (!alive) {
-                if (s >= sEnd) break;
-                cs = (uint32_t)s++;
+                if (STEAL) {
+                    if (have) {                                               // the path that just ended: its radiance into its pixel's tile sum
+                        const float m = fmaxf(fmaxf(sum.x, sum.y), sum.z), lo = fminf(fminf(sum.x, sum.y), sum.z);
+                        if (m < 2048.f && lo >= 0.f) {                        // (false for NaN too)
+                            // 2^-20 fixed point in two 16-bit limbs per channel, each in its own 32-bit word: native 32-bit
+                            // shared-memory atomics (the 64-bit add is a compare-and-swap loop), 65 536 samples before a limb can wrap
+                            const uint32_t vx = __float2uint_rn(sum.x * 1048576.f), vy = __float2uint_rn(sum.y * 1048576.f), vz = __float2uint_rn(sum.z * 1048576.f);
+                            atomicAdd(&tileSum[warp][slot][0], vx & 0xFFFFu); atomicAdd(&tileSum[warp][slot][1], vx >> 16);
+                            atomicAdd(&tileSum[warp][slot][2], vy & 0xFFFFu); atomicAdd(&tileSum[warp][slot][3], vy >> 16);
+                            atomicAdd(&tileSum[warp][slot][4], vz & 0xFFFFu); atomicAdd(&tileSum[warp][slot][5], vz >> 16);
+                        } else if (m != m || lo != lo) atomicOr(&tileNaN[warp], 1u << slot);
+                        else atomicOr(&tileInf[warp], 1u << slot);            // beyond the fixed-point range: the pixel saturates
+                        sum = f3(0.f, 0.f, 0.f);
+                    }
+                    const uint32_t idx = atomicAdd(&tileNext[warp], 1u);
+                    if (idx >= tileTotal) break;
+                    uint32_t sm;
+                    if (tileCnt == 32) { slot = idx & 31u; sm = idx >> 5; }
+                    else { sm = idx / (uint32_t)tileCnt; slot = __fns(insideMask, 0u, (int)(idx - sm * (uint32_t)tileCnt) + 1); }
+                    cs = (uint32_t)s + sm;
+                    col = blockIdx.x * 16 + (warp & 1) * 8 + (int)(slot & 7u);
+                    row = blockIdx.y * (MEGA_BLOCK / 16) + (warp >> 1) * 4 + (int)(slot >> 3);
+                    jUp = p.H - 1 - row;
+                    pix = (uint32_t)(row * p.W + col);
+                    have = true;
+                } else {
+                    if (s >= sEnd) break;
+                    cs = (uint32_t)s++;
+                }
                 depth = 0;
             }
             uint4 r = make_uint4(0u, 0u, 0u, 0u);
@@ -128,12 +180,26 @@ __global__ void __launch_bounds__(MEGA_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_me
             hitPid = h.pid;
             alive = true;                                                     // scatter at the top of the next iteration (sf, D = incoming direction)
         }
-        // each z chunk owns its own plane of the accumulation target (planeStride = 0 when there is one chunk):
-        // no atomics, so the sum is deterministic; k_sum_planes folds the planes in fixed order afterwards
-        float4* dst = p.accum + (size_t)blockIdx.z * p.planeStride + pix;
-        float4 a = *dst;
-        a.x += sum.x; a.y += sum.y; a.z += sum.z; a.w += (float)nMine;
-        *dst = a;
+        if (STEAL) {
+            __syncwarp();
+            if (inside) {                                                     // lane L writes pixel slot L of the tile
+                const float k = 1.f / 1048576.f;
+                const unsigned int* t = tileSum[warp][lane];
+                sum = f3((float)((unsigned long long)t[0] + ((unsigned long long)t[1] << 16)) * k, (float)((unsigned long long)t[2] + ((unsigned long long)t[3] << 16)) * k,
+                         (float)((unsigned long long)t[4] + ((unsigned long long)t[5] << 16)) * k);
+                if ((tileInf[warp] >> lane) & 1u) sum = f3(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+                if ((tileNaN[warp] >> lane) & 1u) sum = f3(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+                pix = (uint32_t)(row0 * p.W + col0);
+            }
+        }
+        if (!STEAL || inside) {
+            // each z chunk owns its own plane of the accumulation target (planeStride = 0 when there is one chunk):
+            // no atomics, so the sum is deterministic; k_sum_planes folds the planes in fixed order afterwards
+            float4* dst = p.accum + (size_t)blockIdx.z * p.planeStride + pix;
+            float4 a = *dst;
+            a.x += sum.x; a.y += sum.y; a.z += sum.z; a.w += (float)nMine;
+            *dst = a;
+        }
     }
     if (COUNT) {
         unsigned long long* v = reinterpret_cast<unsigned long long*>(&cnt);
