@@ -696,17 +696,18 @@ def test_gpu_tracks_the_reference_vectors_sample_for_sample(brt):
 
 def test_gpu_full_size_frames_track_the_reference_windows(brt):
     """BASELINE-size frames against the reference itself: the GPU renders the whole 1920x1080 frame of C3 (486 objects, thin lens,
-    depth 10) and C4 (Cornell under the procedural sky, depth 16, ACES) with sampler = reference; inside the windows for which the
+    depth 10) and C4 (Cornell under the procedural sky, depth 16, ACES) and the whole 3840x2160 frame of C5 (the 1 002 528-triangle
+    terrain) with sampler = reference; inside the windows for which the
     reference's own pixel loop was executed (tests/golden/reference_cases_fullsize.json -> reference_vectors.json) the pixels must be
     the reference's: same paths in fp32 instead of float64."""
     from tools import gen_scenes
     G = os.path.join(os.path.dirname(__file__), "golden")
     doc = json.load(open(os.path.join(G, "reference_vectors.json")))
     cases = json.load(open(os.path.join(G, "reference_cases_fullsize.json")))
-    assert len(cases) >= 2
+    assert len(cases) >= 3
     for c in cases:
         W, H, want = c["W"], c["H"], doc["cases"][c["name"]]
-        assert (W, H) == (1920, 1080)
+        assert (W, H) in ((1920, 1080), (3840, 2160))
         x0, y0, x1, y1 = c["rect"]
         rt = brt.RayTracer(W, H, seed=c["seed"])
         assert rt.loadFromJSON(getattr(gen_scenes, c["gen"][0])(**c["gen"][1]))
