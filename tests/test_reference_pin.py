@@ -12,9 +12,10 @@ imports) computes for 20 cases with Math.random replaced by the oracle's Philox 
 
 The cases: the 13 of the second-port cross-check (both fixtures, the four presets, the four backgrounds, all AA / tone-map modes,
 denoise, the orthographic camera) + 7 shaped like the BASELINE configs (fixtures at depth 10, Cornell at depth 16 with ACES and
-denoise, thin-lens random spheres, a terrain mesh under the procedural sky, the duplicate / coplanar tie scene) + 3 windows of
-BASELINE-size frames (reference_cases_fullsize.json: 20x12 pixels of the 1920x1080 C3 and C4 frames, 3x2 pixels of the 3840x2160
-C5 frame with its 1 002 528 triangles; the reference's pixel-loop body run through its own methods)."""
+denoise, thin-lens random spheres, a terrain mesh under the procedural sky, the duplicate / coplanar tie scene) + 5 windows of
+BASELINE-size frames (reference_cases_fullsize.json: C1 600x400 at 16 spp, C2 1280x720, 20x12 pixels of the 1920x1080 C3 and C4
+frames, 3x2 pixels of the 3840x2160 C5 frame with its 1 002 528 triangles; the reference's pixel-loop body run through its own
+methods)."""
 import json
 import os
 
@@ -79,7 +80,7 @@ def test_oracle_matches_the_reference_itself():
     doc = json.load(open(VECTORS))
     ref, exact = doc["cases"], "minijs" in doc.get("generator", "")
     cases = all_cases()
-    assert len(cases) >= 23 and all(c["name"] in ref for c in cases), sorted(set(c["name"] for c in cases) - set(ref))
+    assert len(cases) >= 25 and all(c["name"] in ref for c in cases), sorted(set(c["name"] for c in cases) - set(ref))
     for c in cases:
         name, W, H = c["name"], c["W"], c["H"]
         want = ref[name]
