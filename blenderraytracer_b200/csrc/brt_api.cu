@@ -399,11 +399,13 @@ static int ensure_wide(brt_ctx* ctx) {
     ctx->info.bvh_width = w;
     return BRT_OK;
 }
-// BRUTE reproduces the reference's loops; AUTO takes the hierarchy from 8 bounded primitives up (below that the linear loop wins)
+// BRUTE reproduces the reference's loops; AUTO takes the hierarchy from 6 bounded primitives up.  Measured on a B200
+// (tools/accel_threshold.py, profiles/r02c_accel_threshold.json; 1280x720x32 spp): with 4-5 primitives — the reference's presets — the
+// linear loop wins by 1-17 %, at 6 the hierarchy is 9 % ahead, at 8 22 %, at 16 73 %, at 64 4.5x.
 static bool wants_bvh(const brt_ctx* ctx) {
     if (ctx->rp.accel == BRT_ACCEL_BRUTE) return false;
     if (ctx->rp.accel == BRT_ACCEL_BVH) return ctx->nBounded >= 2;
-    return ctx->nBounded >= 8;
+    return ctx->nBounded >= 6;
 }
 
 static int upload_perm(brt_ctx* ctx) {
