@@ -265,3 +265,50 @@ def test_shim_flattens_the_reference_textured_materials(addon):
     for i in range(d.n_objects):
         if i not in used: assert d.materials[d.objects[i].material].texture == 0
     host.finalize_external(rt.get("_brt"))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="no reference checkout on this machine")
+def test_shim_flattens_the_reference_presets_and_ui_changes(addon):
+    """The scenes a user of the reference actually builds — loadPreset('default' | 'glass' | 'metals' | 'cornell') (ray-tracer.js:282-435:
+    hollow glass sphere with a negative radius, boxes, emissive panels), then UI changes (camera preset, background, resize) — reach
+    libbrt as the live objects are: compared with a field-by-field dump of the SAME live World / Camera after each render() call."""
+    from make_host_fixtures_minijs import dump_state
+    from test_reference_host_pin import check_state
+    lib = brt.load()
+    interp, host, shim = node_like(addon)
+    RayTracer = interp.load_module("/root/reference/js/ray-tracer.js")["RayTracer"]
+    interp.call(shim["installGpuRender"], J.UNDEF, [RayTracer, J.py_to_js({"device": -1})])
+    rt = interp.construct(RayTracer, [fake_canvas(600, 400, [])])
+    interp.globals.vars["window"].set("renderCancelled", False)
+
+    def render_and_compare(what, bg_kind, bg_color=None, bg_intensity=1.0):
+        with pytest.raises(J.JSThrow):
+            interp.call(rt.get("render"), rt, [J.native(lambda t, a: J.UNDEF)])
+        assert not host.log, (what, host.log)
+        st = dump_state(rt)
+        st["background"] = {0: "bound skyGradient", 1: "bound solidBackground", 2: "bound hdriBackground", 3: "bound proceduralSky"}[bg_kind]
+        check_state(lib, ctx_of(rt), st, what, derived_only=True)
+        kind, col, inten = C.c_int(), (C.c_double * 3)(), C.c_double()
+        lib.brt_get_background(ctx_of(rt), C.byref(kind), col, C.byref(inten))
+        assert (kind.value, inten.value) == (bg_kind, bg_intensity), what
+        if bg_color is not None: assert tuple(col) == bg_color, what
+        p = L.brt_render_params()
+        lib.brt_get_render_params(ctx_of(rt), C.byref(p))
+        assert (p.width, p.height) == (st["width"], st["height"]), what
+
+    render_and_compare("constructor's default scene", 0)
+    for preset, kind, color in (("glass", 0, None), ("metals", 0, None), ("cornell", 1, (0.0, 0.0, 0.0)), ("default", 0, None)):
+        interp.call(rt.get("loadPreset"), rt, [preset])
+        render_and_compare("preset " + preset, kind, color)
+    assert any(o["cls"] == "Sphere" and o["radius"] < 0 for o in (interp.call(rt.get("loadPreset"), rt, ["glass"]), dump_state(rt))[1]["objects"])
+    render_and_compare("glass again (hollow sphere: negative radius)", 0)
+    interp.call(rt.get("loadCameraPreset"), rt, ["close-up"]); render_and_compare("camera preset close-up", 0)
+    interp.call(rt.get("updateBackground"), rt, ["procedural_sky", 0.5]); render_and_compare("procedural sky", 3, None, 0.5)
+    interp.call(rt.get("updateBackground"), rt, ["solid", 2.0]); render_and_compare("solid background", 1, (0.1, 0.1, 0.1), 2.0)
+    interp.call(rt.get("resizeCanvas"), rt, [320.0, 200.0]); render_and_compare("resized canvas", 1, (0.1, 0.1, 0.1), 2.0)
+    interp.call(rt.get("updateRenderSettings"), rt, [J.py_to_js(dict(samples=9, maxBounces=7, toneMapping="aces", antiAliasing="stochastic", gamma=1.8, exposure=1.5))])
+    render_and_compare("render settings", 1, (0.1, 0.1, 0.1), 2.0)
+    p = L.brt_render_params()
+    lib.brt_get_render_params(ctx_of(rt), C.byref(p))
+    assert (p.spp, p.max_depth, p.tonemap, p.aa_mode, p.gamma, p.exposure) == (9, 7, 1, 2, 1.8, 1.5)
+    host.finalize_external(rt.get("_brt"))
