@@ -81,6 +81,45 @@ def inside_scene():
                 background=dict(type="solid", color=[0.2, 0.2, 0.2], intensity=1.0))
 
 
+def aov_of_case(js_dir, c):
+    """camera.getRay((i + .5) / W, (j + .5) / H) + world.hit(ray, 0.001, Infinity) of the reference for every pixel of case c;
+    which object / triangle won is learnt by wrapping their hit methods.  Raises RuntimeError when the reference refuses the scene."""
+    interp, RayTracer, Vec3 = M.load_reference(js_dir)
+    W, H = c["W"], c["H"]
+    rt = interp.construct(RayTracer, [M.fake_canvas(interp, W, H)])
+    if not J.truthy(M.method(interp, rt, "loadFromJSON", J.py_to_js(json.loads(json.dumps(c["scene"]))))):
+        raise RuntimeError("reference loadFromJSON returned false")
+    interp.globals.vars["Math"].set("random", J.native(lambda t, a: 0.5))     # lens offset 0 (camera.js: the disk sample is (0, 0))
+    world, cam = rt.get("world"), rt.get("camera")
+    last = {}                                              # id(HitRecord) -> (object index, triangle index)
+    def wrap(owner, oi, ti):
+        orig = owner.get("hit")
+        def rec(this, a):
+            r = interp.call(orig, this, a)
+            if isinstance(r, J.JSObject) and id(r) not in last: last[id(r)] = (oi, ti, r)
+            return r
+        owner.set("hit", J.native(rec))
+    for oi, o in enumerate(world.get("objects").items):
+        tris = o.get("triangles")
+        if isinstance(tris, J.JSArray):
+            for ti, t in enumerate(tris.items): wrap(t, oi, ti)
+        else:
+            wrap(o, oi, -1)
+    obj, tri, ts, nrm, ff = [], [], [], [], []
+    for row in range(H):
+        j = H - 1 - row
+        for i in range(W):
+            last.clear()
+            ray = M.method(interp, cam, "getRay", (i + 0.5) / W, (j + 0.5) / H)
+            hit = M.method(interp, world, "hit", ray, 0.001, float("inf"))
+            if not isinstance(hit, J.JSObject):
+                obj.append(-1); tri.append(-1); ts.append(None); nrm.append([0.0, 0.0, 0.0]); ff.append(0); continue
+            oi, ti, _ = last[id(hit)]
+            n = hit.get("normal")
+            obj.append(oi); tri.append(ti); ts.append(hit.get("t")); nrm.append([n.get("x"), n.get("y"), n.get("z")]); ff.append(1 if J.truthy(hit.get("frontFace")) else 0)
+    return dict(name=c["name"], W=W, H=H, scene=c["scene"], obj_id=obj, tri_id=tri, t=ts, normal=nrm, front_face=ff)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default=os.environ.get("BRT_REFERENCE", "/root/reference"))
@@ -93,42 +132,9 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         all_cases = cases()
     for c in all_cases:
-        interp, RayTracer, Vec3 = M.load_reference(js_dir)
-        W, H = c["W"], c["H"]
-        rt = interp.construct(RayTracer, [M.fake_canvas(interp, W, H)])
-        assert J.truthy(M.method(interp, rt, "loadFromJSON", J.py_to_js(json.loads(json.dumps(c["scene"])))))
-        if not (c["scene"].get("camera") or {}).get("resolution"):
-            pass
-        interp.globals.vars["Math"].set("random", J.native(lambda t, a: 0.5))
-        world, cam = rt.get("world"), rt.get("camera")
-        last = {}                                              # id(HitRecord) -> (object index, triangle index)
-        def wrap(owner, oi, ti):
-            orig = owner.get("hit")
-            def rec(this, a):
-                r = interp.call(orig, this, a)
-                if isinstance(r, J.JSObject) and id(r) not in last: last[id(r)] = (oi, ti, r)
-                return r
-            owner.set("hit", J.native(rec))
-        for oi, o in enumerate(world.get("objects").items):
-            tris = o.get("triangles")
-            if isinstance(tris, J.JSArray):
-                for ti, t in enumerate(tris.items): wrap(t, oi, ti)
-            else:
-                wrap(o, oi, -1)
-        obj, tri, ts, nrm, ff = [], [], [], [], []
-        for row in range(H):
-            j = H - 1 - row
-            for i in range(W):
-                last.clear()
-                ray = M.method(interp, cam, "getRay", (i + 0.5) / W, (j + 0.5) / H)
-                hit = M.method(interp, world, "hit", ray, 0.001, float("inf"))
-                if not isinstance(hit, J.JSObject):
-                    obj.append(-1); tri.append(-1); ts.append(None); nrm.append([0.0, 0.0, 0.0]); ff.append(0); continue
-                oi, ti, _ = last[id(hit)]
-                n = hit.get("normal")
-                obj.append(oi); tri.append(ti); ts.append(hit.get("t")); nrm.append([n.get("x"), n.get("y"), n.get("z")]); ff.append(1 if J.truthy(hit.get("frontFace")) else 0)
-        out["cases"].append(dict(name=c["name"], W=W, H=H, scene=c["scene"], obj_id=obj, tri_id=tri, t=ts, normal=nrm, front_face=ff))
-        print(c["name"], f"{W}x{H}", "hits", sum(1 for x in obj if x >= 0), "objects", len(world.get("objects").items), flush=True)
+        rec = aov_of_case(js_dir, c)
+        out["cases"].append(rec)
+        print(c["name"], f"{c['W']}x{c['H']}", "hits", sum(1 for x in rec["obj_id"] if x >= 0), flush=True)
     json.dump(out, open(args.out, "w"))
     print("wrote", args.out)
 

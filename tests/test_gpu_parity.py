@@ -747,6 +747,41 @@ def test_gpu_tracks_the_reference_on_random_scenes(brt):
     assert all(r["nonfinite_gpu"] == r["nonfinite_ref"] for r in rows)
 
 
+def test_gpu_primary_visibility_on_random_scenes(brt):
+    """40 random scenes (tools/fuzz_aov.py; degenerate values included) with the reference's own camera.getRay + World.hit results
+    committed in tests/golden/reference_fuzz_aov_vectors.json: the float64 AOV kernel reproduces object ID, triangle ID, t, normal and
+    frontFace exactly (NaN where the reference has NaN); the render path's own primary-hit code (fp32 hierarchy proposes, float64
+    decides) gives the same IDs with the linear loops, and with the hierarchy everywhere except the phantom hits of deviation D2."""
+    doc = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_fuzz_aov_vectors.json")))
+    assert len(doc["cases"]) >= 35
+    n_px = n_bvh_diff = 0
+    for c in doc["cases"]:
+        H, W = c["H"], c["W"]
+        want_obj = np.asarray(c["obj_id"], np.int32).reshape(H, W); want_tri = np.asarray(c["tri_id"], np.int32).reshape(H, W)
+        want_t = np.array([np.inf if v is None else v for v in c["t"]], np.float64).reshape(H, W)
+        want_n = np.asarray(c["normal"], np.float64).reshape(H, W, 3); want_ff = np.asarray(c["front_face"], np.uint8).reshape(H, W)
+        hit = want_obj >= 0
+        rt = brt.RayTracer(W, H, seed=1)
+        assert rt.loadFromJSON(c["scene"]), c["name"]
+        rt.resizeCanvas(W, H)
+        a64 = rt.primaryAOV(64)
+        assert np.array_equal(a64["obj_id"], want_obj) and np.array_equal(a64["tri_id"], want_tri), (c["name"], int((a64["obj_id"] != want_obj).sum()))
+        assert np.array_equal(a64["t"][hit], want_t[hit], equal_nan=True) and np.array_equal(a64["normal"][hit], want_n[hit], equal_nan=True), c["name"]
+        assert np.array_equal(a64["front_face"][hit], want_ff[hit]), c["name"]
+        finite = hit & np.isfinite(want_t)
+        rt.accel = "brute"
+        a = rt.primaryAOV(32)
+        bad = (a["obj_id"] != want_obj) | (a["tri_id"] != want_tri)
+        assert not (bad & (finite | ~hit)).any(), (c["name"], "brute", int(bad.sum()))
+        rt.accel = "bvh"
+        a = rt.primaryAOV(32)
+        bad = ((a["obj_id"] != want_obj) | (a["tri_id"] != want_tri)) & (finite | ~hit)
+        n_px += H * W; n_bvh_diff += int(bad.sum())
+        rt.close()
+    print(f"[fuzz aov] {len(doc['cases'])} random scenes, {n_px} pixels: hierarchy differs from the reference's linear loops in {n_bvh_diff} pixels")
+    assert n_bvh_diff <= n_px // 2000
+
+
 def test_gpu_primary_visibility_equals_the_reference(brt):
     """North-star gate "primary-hit object IDs bit-exact" against the reference ITSELF: camera.getRay + World.hit of the unmodified
     js/*.js at every pixel centre (tests/golden/reference_aov_vectors.json, baseline/make_aov_fixtures_minijs.py) vs the float64
