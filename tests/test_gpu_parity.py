@@ -731,8 +731,7 @@ def test_gpu_tracks_the_reference_on_random_scenes(brt):
     """36 random scenes (tools/fuzz_render.py: every primitive / material kind, degenerate values, any camera, background, AA and
     tone-map mode, denoise) whose reference outputs — the unmodified js/*.js under the interpreter, bit-identical to the oracle — are
     committed in tests/golden/reference_fuzz_vectors.json: the CUDA path with sampler = reference gives the same RGBA8.  Measured on a
-    B200 (profiles/r02c_parity_fuzz_gpu.json): 33 of 36 scenes identical on every pixel, 99.7 % of all pixels; the outlier (89.6 %)
-    has its camera and a mesh vertex at coordinates of 1e6, where fp32 secondary rays resolve 0.06 units."""
+    B200 (profiles/r02c_parity_fuzz_gpu.json): all 36 scenes identical on every pixel."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import parity_fuzz_gpu
@@ -743,7 +742,7 @@ def test_gpu_tracks_the_reference_on_random_scenes(brt):
     share = sum(r["identical"] * r["pixels"] for r in rows) / tot
     exact = sum(r["identical"] == 1.0 for r in rows)
     print(f"[fuzz] {exact} of {len(rows)} random scenes identical on every pixel; {share:.4f} of {tot} pixels identical; worst {min(r['identical'] for r in rows):.3f}")
-    assert share >= 0.99 and exact >= 30 and min(r["identical"] for r in rows) >= 0.85, [r for r in rows if r["identical"] < 1.0]
+    assert share >= 0.995 and exact >= 34 and min(r["identical"] for r in rows) >= 0.95, [r for r in rows if r["identical"] < 1.0]
     assert all(r["nonfinite_gpu"] == r["nonfinite_ref"] for r in rows)
 
 
@@ -762,8 +761,7 @@ def test_gpu_primary_visibility_on_random_scenes(brt):
         want_n = np.asarray(c["normal"], np.float64).reshape(H, W, 3); want_ff = np.asarray(c["front_face"], np.uint8).reshape(H, W)
         hit = want_obj >= 0
         rt = brt.RayTracer(W, H, seed=1)
-        assert rt.loadFromJSON(c["scene"]), c["name"]
-        rt.resizeCanvas(W, H)
+        assert rt.loadFromJSON(c["scene"]), c["name"]                     # (no resizeCanvas: that would rebuild the camera from its derived vectors)
         a64 = rt.primaryAOV(64)
         assert np.array_equal(a64["obj_id"], want_obj) and np.array_equal(a64["tri_id"], want_tri), (c["name"], int((a64["obj_id"] != want_obj).sum()))
         assert np.array_equal(a64["t"][hit], want_t[hit], equal_nan=True) and np.array_equal(a64["normal"][hit], want_n[hit], equal_nan=True), c["name"]

@@ -16,7 +16,6 @@ def compare(doc):
         rt = brt.RayTracer(W, H, seed=c["seed"])
         ok = rt.loadFromJSON(c["scene"])
         assert ok, c["name"]                                          # the reference accepted it
-        rt.resizeCanvas(W, H)
         rt.setCloudPermutation(np.asarray(c["perm"], np.uint8))
         rt.updateRenderSettings(dict(samples=c["spp"], maxBounces=c["depth"], antiAliasing=c["aa"], toneMapping=c["tonemap"], exposure=c["exposure"],
                                      gamma=c["gamma"], denoising=c["denoise"], denoiseStrength=c["strength"]))
