@@ -44,8 +44,11 @@ class brt_light(C.Structure):
     _fields_ = [("type", C.c_int32), ("_pad", C.c_int32), ("v", d3), ("color", d3), ("intensity", C.c_double)]
 
 
+SCENE_CONSTRUCTED = 1   # brt_scene_desc.flags: rows read from constructed objects (stored as they are)
+
+
 class brt_scene_desc(C.Structure):
-    _fields_ = [("objects", C.POINTER(brt_object)), ("n_objects", C.c_int32), ("_pad0", C.c_int32),
+    _fields_ = [("objects", C.POINTER(brt_object)), ("n_objects", C.c_int32), ("flags", C.c_int32),
                 ("materials", C.POINTER(brt_material)), ("n_materials", C.c_int32), ("_pad1", C.c_int32),
                 ("mesh_triangles", C.POINTER(C.c_double)), ("n_mesh_triangles", C.c_int64),
                 ("lights", C.POINTER(brt_light)), ("n_lights", C.c_int32), ("_pad2", C.c_int32),

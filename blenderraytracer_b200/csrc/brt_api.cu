@@ -178,12 +178,13 @@ int brt_scene_set_flat(brt_ctx* ctx, const brt_scene_desc* d) {
     sc.materials.assign(d->materials, d->materials + d->n_materials);
     sc.lights.assign(d->lights, d->lights + d->n_lights);
     if (d->n_textures) sc.textures.assign(d->textures, d->textures + d->n_textures);
-    for (brt_object& o : sc.objects) if (o.type == BRT_OBJ_PLANE) {               // geometry.js:52
+    const bool raw = !(d->flags & BRT_SCENE_CONSTRUCTED);             // constructor arguments: apply what the reference's constructors do
+    if (raw) for (brt_object& o : sc.objects) if (o.type == BRT_OBJ_PLANE) {      // geometry.js:52
         double l = std::sqrt(o.b[0] * o.b[0] + o.b[1] * o.b[1] + o.b[2] * o.b[2]);
         if (l > 0) { o.b[0] /= l; o.b[1] /= l; o.b[2] /= l; } else o.b[0] = o.b[1] = o.b[2] = 0;
     }
-    for (brt_material& m : sc.materials) if (m.type == BRT_MAT_METAL && !(m.param != m.param)) m.param = std::fmin(m.param, 1.0);   // materials.js:33
-    for (brt_light& l : sc.lights) if (l.type == BRT_LIGHT_DIRECTIONAL) {         // lights.js:38
+    if (raw) for (brt_material& m : sc.materials) if (m.type == BRT_MAT_METAL && !(m.param != m.param)) m.param = std::fmin(m.param, 1.0);   // materials.js:33
+    if (raw) for (brt_light& l : sc.lights) if (l.type == BRT_LIGHT_DIRECTIONAL) {   // lights.js:38
         double n = std::sqrt(l.v[0] * l.v[0] + l.v[1] * l.v[1] + l.v[2] * l.v[2]);
         if (n > 0) { l.v[0] /= n; l.v[1] /= n; l.v[2] /= n; } else l.v[0] = l.v[1] = l.v[2] = 0;
     }
@@ -451,6 +452,7 @@ int brt_scene_get_flat(brt_ctx* ctx, brt_scene_desc* out) {
     out->mesh_triangles = s.meshTris.data(); out->n_mesh_triangles = (int64_t)(s.meshTris.size() / 9);
     out->lights = s.lights.data(); out->n_lights = (int)s.lights.size();
     out->textures = s.textures.data(); out->n_textures = (int)s.textures.size();
+    out->flags = BRT_SCENE_CONSTRUCTED;                             // what the ctx holds is post-constructor: get -> set round-trips exactly
     return BRT_OK;
 }
 

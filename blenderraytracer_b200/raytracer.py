@@ -449,6 +449,7 @@ class RayTracer:
         if d.n_textures:
             C.memmove(texs, d.textures, C.sizeof(L.brt_texture) * d.n_textures)
         out.textures, out.n_textures = texs, d.n_textures
+        out.flags = d.flags                                        # BRT_SCENE_CONSTRUCTED: post-constructor values, stored as they are on the way back
         return out, (objs, mats, lights, tris, texs)
 
     def setSceneFlat(self, desc_keep):

@@ -112,8 +112,14 @@ typedef struct brt_light {
     double intensity;
 } brt_light;
 
+/* flags: 0 = the rows are CONSTRUCTOR ARGUMENTS (new Plane(point, normal), new DirectionalLight(direction, ...), new Metal(albedo,
+ * roughness)): the library applies what those constructors do — plane normals and directional-light directions are normalised
+ * (geometry.js:52, lights.js:38), metal roughness is clamped to 1 (materials.js:33).  BRT_SCENE_CONSTRUCTED = the rows were read
+ * from CONSTRUCTED objects (the JS shim flattening a live World; brt_scene_get_flat): they are stored as they are — normalising a
+ * normalised vector a second time moves its last bit. */
+#define BRT_SCENE_CONSTRUCTED 1
 typedef struct brt_scene_desc {
-    const brt_object* objects;      int32_t n_objects;     int32_t _pad0;
+    const brt_object* objects;      int32_t n_objects;     int32_t flags;
     const brt_material* materials;  int32_t n_materials;   int32_t _pad1;
     const double* mesh_triangles;   /* 9 doubles per triangle: v0.xyz v1.xyz v2.xyz */
     int64_t n_mesh_triangles;

@@ -104,9 +104,10 @@ static napi_value js_load_scene_json(napi_env env, napi_callback_info info) {
 /* setSceneFlat(ctx, objects Float64Array[13 n], materials Float64Array[6 m], meshTris Float64Array[9 t], lights Float64Array[8 l])
  * objects: type, material, a.xyz, b.xyz, c.xyz, firstTri, triCount — one row per world.objects entry, in order (world.js:24-30)
  * materials: type, r, g, b, param, texture(1-based, 0 = none) — 6 per material
- * optional: textures Float64Array[8 k] (kind, odd.rgb, even.rgb, scale) + texturePerms Uint8Array[256 k]   (js/textures.js) */
+ * optional: textures Float64Array[8 k] (kind, odd.rgb, even.rgb, scale) + texturePerms Uint8Array[256 k]   (js/textures.js);
+ * flags (number): BRT_SCENE_CONSTRUCTED = 1 when the rows were read from constructed objects (normals already normalised) */
 static napi_value js_set_scene_flat(napi_env env, napi_callback_info info) {
-    ARGS(7);
+    ARGS(8);
     brt_ctx* ctx = get_ctx(env, argv[0]);
     size_t no, nm, nt, nl;
     double* o = f64_array(env, argv[1], &no); double* m = f64_array(env, argv[2], &nm);
@@ -138,6 +139,7 @@ static napi_value js_set_scene_flat(napi_env env, napi_callback_info info) {
     d.objects = objs; d.n_objects = (int32_t)no; d.materials = mats; d.n_materials = (int32_t)nm;
     d.mesh_triangles = t; d.n_mesh_triangles = (int64_t)nt; d.lights = lights; d.n_lights = (int32_t)nl;
     d.textures = texs; d.n_textures = (int32_t)nx;
+    if (argc >= 8) { int32_t fl = 0; if (napi_get_value_int32(env, argv[7], &fl) == napi_ok) d.flags = fl; }   /* 1 = rows read from constructed objects */
     int rc = brt_scene_set_flat(ctx, &d);                       /* borrowed, copied before return */
     free(objs); free(mats); free(lights); free(texs);
     if (rc != BRT_OK) return throw_brt(env, ctx, rc);

@@ -119,7 +119,9 @@ export function installGpuRender(RayTracer, { device = 0, devices = undefined, s
     this._brt ??= addon.create(devices ?? device);                  // an array: brt_create_multi, samples split over the GPUs
     const ctx = this._brt;
     const flat = flattenWorld(this.world);
-    addon.setSceneFlat(ctx, flat.objects, flat.materials, flat.tris, flat.lights, flat.textures, flat.perms);
+    // 1 = BRT_SCENE_CONSTRUCTED: these are members of constructed objects (Plane.normal and DirectionalLight.direction are already
+    // normalised, Metal.roughness already clamped): libbrt must store them as they are
+    addon.setSceneFlat(ctx, flat.objects, flat.materials, flat.tris, flat.lights, flat.textures, flat.perms, 1);
     addon.setCameraDerived(ctx, flattenCamera(this.camera));
     const bg = backgroundOf(this);
     const perm = this.world.cloudNoise ? Uint8Array.from(this.world.cloudNoise.p.slice(0, 256)) : undefined;

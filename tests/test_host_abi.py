@@ -258,6 +258,31 @@ def test_flat_scene_roundtrip_and_validation(host):
     info = L.brt_scene_info()
     assert lib.brt_scene_info_get(h, C.byref(info)) == L.BRT_OK
     assert (info.n_objects, info.n_spheres, info.n_planes, info.n_boxes, info.n_triangles) == (4, 1, 1, 1, 1)
+    # BRT_SCENE_CONSTRUCTED: rows read from constructed objects are stored as they are (a second normalisation moves the last bit of
+    # a vector such as (1.179, 1e6, 0.001) / |.|); brt_scene_get_flat hands back post-constructor values with the flag set, so that
+    # get -> set round-trips exactly
+    w2 = brt.World()
+    w2.add(brt.Plane((0, 0, 0), (1.179, 1000000.0, 0.001), brt.Metal((0.5, 0.5, 0.5), 7.0)))
+    w2.addLight(brt.DirectionalLight((0.3, -1.7, 0.2), (1, 1, 1), 1))
+    d2, keep2 = w2.flatten()
+    assert d2.flags == 0 and lib.brt_scene_set_flat(h, C.byref(d2)) == L.BRT_OK
+    objs, mats, lights, _ = _flat(lib, h)
+    n1, l1 = list(objs[0].b), list(lights[0].v)
+    assert abs(np.linalg.norm(n1) - 1) < 1e-15 and mats[0].param == 1.0
+    got = L.brt_scene_desc()
+    assert lib.brt_scene_get_flat(h, C.byref(got)) == L.BRT_OK and got.flags == L.SCENE_CONSTRUCTED
+    for _ in range(3):                                                                   # any number of round trips: bit-stable
+        rt_desc = L.brt_scene_desc()
+        assert lib.brt_scene_get_flat(h, C.byref(rt_desc)) == L.BRT_OK
+        o2 = (L.brt_object * 1)(rt_desc.objects[0]); m2 = (L.brt_material * 1)(rt_desc.materials[0]); li2 = (L.brt_light * 1)(rt_desc.lights[0])
+        back = L.brt_scene_desc(); back.objects, back.n_objects, back.materials, back.n_materials, back.lights, back.n_lights = o2, 1, m2, 1, li2, 1
+        back.flags = L.SCENE_CONSTRUCTED
+        assert lib.brt_scene_set_flat(h, C.byref(back)) == L.BRT_OK
+        objs, mats, lights, _ = _flat(lib, h)
+        assert list(objs[0].b) == n1 and list(lights[0].v) == l1
+    raw = (L.brt_object * 1)(objs[0]); raw[0].b[0], raw[0].b[1], raw[0].b[2] = 0.0, 3.0, 0.0
+    back.objects, back.flags = raw, L.SCENE_CONSTRUCTED
+    assert lib.brt_scene_set_flat(h, C.byref(back)) == L.BRT_OK and list(_flat(lib, h)[0][0].b) == [0.0, 3.0, 0.0]   # as is: the caller said so
     # validation
     bad = L.brt_scene_desc(); bad.n_objects = 1
     assert lib.brt_scene_set_flat(h, C.byref(bad)) == L.BRT_E_INVALID

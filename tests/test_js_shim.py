@@ -312,3 +312,38 @@ def test_shim_flattens_the_reference_presets_and_ui_changes(addon):
     lib.brt_get_render_params(ctx_of(rt), C.byref(p))
     assert (p.spp, p.max_depth, p.tonemap, p.aa_mode, p.gamma, p.exposure) == (9, 7, 1, 2, 1.8, 1.5)
     host.finalize_external(rt.get("_brt"))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="no reference checkout on this machine")
+def test_shim_flattening_on_random_scenes(addon):
+    """120 random scenes (tools/fuzz_ingest.py's generator: empty meshes, filtered triangles, unknown types, zero normals, every light
+    and background kind ...) loaded by the reference's own loader, flattened by the shim, handed to libbrt through the real addon:
+    the context then holds exactly what a dump of the live World / Camera says."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_ingest
+    from make_host_fixtures_minijs import dump_state
+    from test_reference_host_pin import check_state
+    lib = brt.load()
+    interp, host, shim = node_like(addon)
+    RayTracer = interp.load_module("/root/reference/js/ray-tracer.js")["RayTracer"]
+    interp.call(shim["installGpuRender"], J.UNDEF, [RayTracer, J.py_to_js({"device": -1})])
+    interp.globals.vars["window"].set("renderCancelled", False)
+    r = random.Random(17)
+    n = 0
+    for k in range(120):
+        scene = fuzz_ingest.gen_scene(r)
+        if scene.get("camera"): scene["camera"].pop("resolution", None)     # keeps imageData small: the host mirrors it into a C buffer per call
+        rt = interp.construct(RayTracer, [fake_canvas(64, 40, [])])
+        if not J.truthy(interp.call(rt.get("loadFromJSON"), rt, [J.py_to_js(json.loads(json.dumps(scene)))])):
+            continue
+        with pytest.raises(J.JSThrow) as e:
+            interp.call(rt.get("render"), rt, [J.native(lambda t, a: J.UNDEF)])
+        assert "no CPU fallback" in J.to_str(e.value.value.get("message")) and not host.log, (k, J.to_str(e.value.value.get("message")), host.log, scene)
+        st = dump_state(rt)
+        bg = (scene.get("background") or {}).get("type")
+        st["background"] = {"solid": "bound solidBackground", "hdri": "bound hdriBackground", "procedural_sky": "bound proceduralSky"}.get(bg, "bound skyGradient")
+        check_state(lib, ctx_of(rt), st, f"shim fuzz {k}", derived_only=True)
+        host.finalize_external(rt.get("_brt"))
+        n += 1
+    assert n >= 100
