@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(MEGA_BLOCK, PT_MIN_BLOCKS_MEGA) k_pathtrace_me
                         else atomicOr(&tileInf[warp], 1u << slot);            // beyond the fixed-point range: the pixel saturates
                         sum = f3(0.f, 0.f, 0.f);
                     }
-                    const uint32_t idx = atomicAdd(&tileNext[warp], 1u);
+                    const uint32_t idx = atomicAdd(&tileNext[warp], 1u);     // (one warp-aggregated add — ballot, leader, shuffle — measured slower: C3 +0.3 % instead of +1.6 %)
                     if (idx >= tileTotal) break;
                     uint32_t sm;
                     if (tileCnt == 32) { slot = idx & 31u; sm = idx >> 5; }
