@@ -283,3 +283,36 @@ def test_pathologically_deep_lbvh_uses_the_hybrid_stack(brt):
                  background=dict(type="gradient"))
     rt, _ = _check(brt, scene, 150, 100, spp=4, depth=6)
     assert rt.sceneInfo()["bvh_depth"] > 32, rt.sceneInfo()["bvh_depth"]
+
+
+def test_every_kernel_variant_survives_the_random_scenes(brt):
+    """The 36 random degenerate scenes of tests/golden/reference_fuzz_vectors.json (zero radii, zero normals, fov 0, coordinates of
+    1e6, filtered-out meshes, unknown types ...) through the FAST sampler and every traversal variant: no error, and the linear
+    loops, the binary hierarchy and its 4- / 8-wide collapses give bit-identical images (the hierarchy is invisible), also with
+    the wavefront integrator up to fp32 summation order."""
+    import json, os
+    doc = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_fuzz_vectors.json")))
+    n_bvh = 0
+    for e in doc["cases"]:
+        c = e["case"]
+        W, H = c["W"], c["H"]
+        rt = brt.RayTracer(W, H, seed=c["seed"])
+        assert rt.loadFromJSON(c["scene"]), c["name"]
+        rt.setCloudPermutation(np.asarray(c["perm"], np.uint8))
+        rt.updateRenderSettings(dict(samples=4, maxBounces=c["depth"], antiAliasing=c["aa"], toneMapping=c["tonemap"], exposure=c["exposure"], gamma=c["gamma"]))
+        rt.sampler, rt.accel = "fast", "brute"
+        base = rt.render(want_linear=True).copy(); lin = rt.linearMean.copy()
+        info = rt.sceneInfo()
+        if info["n_spheres"] + info["n_boxes"] + info["n_triangles"] >= 2:
+            n_bvh += 1
+            rt.accel = "bvh"
+            for width in (2, 4, 8):
+                rt.bvhWidth = width
+                img = rt.render(want_linear=True)
+                assert np.array_equal(img, base) and np.array_equal(rt.linearMean, lin, equal_nan=True), (c["name"], width)
+            rt.bvhWidth = 0
+            rt.integrator = "wavefront"
+            img = rt.render()
+            assert (np.abs(img.astype(int) - base.astype(int)) <= 1).mean() >= 0.99, c["name"]
+        rt.close()
+    assert n_bvh >= 10
