@@ -43,3 +43,10 @@ def sample_mesh():
 def kat():
     with open(os.path.join(GOLDEN, "kat.json")) as f:
         return json.load(f)
+
+# a checkout of Shinzef/BlenderRayTracer, when this machine has one (the build container; never the GPU box): the tests that execute
+# the reference's own JavaScript run against it, everything else uses the committed vectors.  BRT_REFERENCE overrides the location.
+REFERENCE = os.environ.get("BRT_REFERENCE", "/root/reference")
+REFERENCE_JS = os.path.join(REFERENCE, "js")
+HAVE_REFERENCE = os.path.isdir(REFERENCE_JS)
+

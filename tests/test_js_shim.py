@@ -18,7 +18,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, HAVE_REFERENCE, REFERENCE, REFERENCE_JS
 import blenderraytracer_b200 as brt
 from blenderraytracer_b200 import _lib as L
 
@@ -29,7 +29,7 @@ sys.path.insert(0, NAPI)
 import minijs as J  # noqa: E402
 import napi_host  # noqa: E402
 
-HAVE_REF = os.path.isdir("/root/reference/js")
+HAVE_REF = HAVE_REFERENCE
 
 
 @pytest.fixture(scope="module")
@@ -73,7 +73,7 @@ def test_shim_on_the_reference_classes_hands_libbrt_the_reference_objects(addon)
     n = 0
     for c in doc["cases"]:
         interp, host, shim = node_like(addon)
-        RayTracer = interp.load_module("/root/reference/js/ray-tracer.js")["RayTracer"]
+        RayTracer = interp.load_module(os.path.join(REFERENCE_JS, "ray-tracer.js"))["RayTracer"]
         interp.call(shim["installGpuRender"], J.UNDEF, [RayTracer, J.py_to_js({"device": -1})])     # host-only libbrt context: everything but the kernels
         rt = interp.construct(RayTracer, [fake_canvas(c["W"], c["H"], [])])
         oks = [J.truthy(interp.call(rt.get("loadFromJSON"), rt, [J.py_to_js(json.loads(json.dumps(s)))])) for s in c["scenes"]]
@@ -229,7 +229,7 @@ def test_shim_flattens_the_reference_textured_materials(addon):
     the texture's own Perlin table (noise.p) of each live object, and the material rows point at it."""
     import make_texture_fixtures_minijs as T
     interp, host, shim = node_like(addon)
-    js = "/root/reference/js"
+    js = REFERENCE_JS
     RayTracer = interp.load_module(js + "/ray-tracer.js")["RayTracer"]
     Vec3 = interp.load_module(js + "/math.js")["Vec3"]
     tex_ex, mat_ex = interp.load_module(js + "/textures.js"), interp.load_module(js + "/materials.js")
@@ -276,7 +276,7 @@ def test_shim_flattens_the_reference_presets_and_ui_changes(addon):
     from test_reference_host_pin import check_state
     lib = brt.load()
     interp, host, shim = node_like(addon)
-    RayTracer = interp.load_module("/root/reference/js/ray-tracer.js")["RayTracer"]
+    RayTracer = interp.load_module(os.path.join(REFERENCE_JS, "ray-tracer.js"))["RayTracer"]
     interp.call(shim["installGpuRender"], J.UNDEF, [RayTracer, J.py_to_js({"device": -1})])
     rt = interp.construct(RayTracer, [fake_canvas(600, 400, [])])
     interp.globals.vars["window"].set("renderCancelled", False)
@@ -326,7 +326,7 @@ def test_shim_flattening_on_random_scenes(addon):
     from test_reference_host_pin import check_state
     lib = brt.load()
     interp, host, shim = node_like(addon)
-    RayTracer = interp.load_module("/root/reference/js/ray-tracer.js")["RayTracer"]
+    RayTracer = interp.load_module(os.path.join(REFERENCE_JS, "ray-tracer.js"))["RayTracer"]
     interp.call(shim["installGpuRender"], J.UNDEF, [RayTracer, J.py_to_js({"device": -1})])
     interp.globals.vars["window"].set("renderCancelled", False)
     r = random.Random(17)

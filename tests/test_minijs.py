@@ -7,6 +7,8 @@ import sys
 
 import pytest
 
+from conftest import HAVE_REFERENCE, REFERENCE, REFERENCE_JS
+
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "baseline"))
 import minijs as J  # noqa: E402
 
@@ -120,11 +122,11 @@ def test_host_modules_and_import_meta(tmp_path):
     assert ex["got"] == "addon:./x.node" and ex["url"] == "file://" + str(tmp_path / "m.mjs") and seen == [ex["url"]]
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine")
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="no reference checkout on this machine")
 def test_reference_math_module_under_the_interpreter():
     """the reference's own Vec3 (js/math.js:6-31), executed from its source: a few identities with exact expectations"""
     interp = J.Interp()
-    ex = interp.load_module("/root/reference/js/math.js")
+    ex = interp.load_module(os.path.join(REFERENCE_JS, "math.js"))
     Vec3 = ex["Vec3"]
     v = interp.construct(Vec3, [1.0, 2.0, 2.0])
     assert interp.call(v.get("length"), v, []) == 3.0

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, HAVE_REFERENCE, REFERENCE, REFERENCE_JS
 import blenderraytracer_b200 as brt
 from blenderraytracer_b200 import _lib as L
 from test_host_abi import _flat, _load, host  # noqa: F401  (host: fixture)
@@ -146,12 +146,12 @@ def test_oracle_lights_match_the_reference():
             assert got[6] == (float("inf") if want["distance"] is None else want["distance"])
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine")
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="no reference checkout on this machine")
 def test_committed_host_vectors_are_what_the_reference_source_computes(tmp_path):
     import subprocess, sys
     out = tmp_path / "host.json"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    subprocess.check_call([sys.executable, os.path.join(root, "baseline", "make_host_fixtures_minijs.py"), "--out", str(out)], stdout=subprocess.DEVNULL)
+    subprocess.check_call([sys.executable, os.path.join(root, "baseline", "make_host_fixtures_minijs.py"), "--out", str(out), "--ref", REFERENCE], stdout=subprocess.DEVNULL)
     new, old = json.load(open(out)), json.load(open(VECTORS))
     assert new["cases"] == old["cases"] and new["lights"] == old["lights"] and new["controls"] == old["controls"]
 
@@ -221,7 +221,7 @@ def test_oracle_controls_equal_the_reference():
     assert n > 100
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine")
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="no reference checkout on this machine")
 def test_native_ingest_equals_the_reference_loader_on_random_scenes():
     """Differential fuzz (tools/fuzz_ingest.py): 150 random scenes with missing fields, zeros, negatives, short / long arrays, odd
     capitalisation, unknown types, out-of-range mesh indices, cameras on top of their target and resolution overrides through the
@@ -230,5 +230,5 @@ def test_native_ingest_equals_the_reference_loader_on_random_scenes():
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
     import fuzz_ingest
-    bad = fuzz_ingest.run(seed=7, n=150)
+    bad = fuzz_ingest.run(seed=7, n=150, ref=REFERENCE)
     assert not bad, bad[:3]

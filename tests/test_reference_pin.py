@@ -22,7 +22,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, HAVE_REFERENCE, REFERENCE, REFERENCE_JS
 from oracle.oracle import OracleRayTracer
 
 VECTORS = os.path.join(GOLDEN, "reference_vectors.json")
@@ -104,7 +104,7 @@ def test_oracle_matches_the_reference_itself():
         assert (rgba[..., 3] == 255).all(), name
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine (the GPU box): the committed vectors are used")
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="no reference checkout on this machine (the GPU box): the committed vectors are used")
 def test_committed_vectors_are_what_the_reference_source_computes():
     """Where the reference checkout exists, two cases are re-executed from its js/*.js and must reproduce the committed vectors."""
     import sys
@@ -115,7 +115,7 @@ def test_committed_vectors_are_what_the_reference_source_computes():
     assert "minijs" in doc["generator"]
     by_name = {c["name"]: c for c in all_cases()}
     for name in ("bg_procedural_sky", "preset_glass"):
-        interp, RayTracer, Vec3 = M.load_reference("/root/reference/js")
+        interp, RayTracer, Vec3 = M.load_reference(REFERENCE_JS)
         got = M.render_seeded(interp, RayTracer, Vec3, by_name[name])
         want = doc["cases"][name]
         assert got["rgba"] == want["rgba"] and got["linear"] == want["linear"] and got["float"] == want["float"], name
@@ -187,7 +187,7 @@ def test_oracle_primary_visibility_matches_the_reference():
         assert np.array_equal(got["front_face"][hit], want["front_face"][hit]), c["name"]
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/js"), reason="no reference checkout on this machine")
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="no reference checkout on this machine")
 def test_oracle_equals_the_reference_on_random_scenes():
     """Differential fuzz of the render path (tools/fuzz_render.py): 25 random small scenes — every primitive and material kind,
     degenerate values (zero radius, zero normals, fov 0, roughness 7, ior 0), any camera / background / AA / tone-map mode, denoise —
@@ -196,5 +196,5 @@ def test_oracle_equals_the_reference_on_random_scenes():
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
     import fuzz_render
-    bad, done = fuzz_render.run(seed=11, n=25)
+    bad, done = fuzz_render.run(seed=11, n=25, ref=REFERENCE)
     assert done >= 20 and not bad, [(k, why) for k, why, _ in bad]
