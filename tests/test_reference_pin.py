@@ -198,3 +198,14 @@ def test_oracle_equals_the_reference_on_random_scenes():
     import fuzz_render
     bad, done = fuzz_render.run(seed=11, n=25, ref=REFERENCE)
     assert done >= 20 and not bad, [(k, why) for k, why, _ in bad]
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="no reference checkout on this machine")
+def test_oracle_textures_equal_the_reference_on_random_textures():
+    """tools/fuzz_textures.py: 150 random textures (all five kinds, random colours / scales incl. 0 and negative / Perlin tables) at 43
+    random points each, incl. negative, huge (1e9) and tiny coordinates: the oracle's texture code gives the reference's bits."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    import fuzz_textures
+    bad = fuzz_textures.run(seed=9, n=150, ref=REFERENCE)
+    assert not bad, bad[:2]
