@@ -163,6 +163,7 @@ def typeof(v):
     if v is NULL: return "object"
     if isinstance(v, bool): return "boolean"
     if isinstance(v, float): return "number"
+    if isinstance(v, int): return "bigint"
     if isinstance(v, str): return "string"
     if isinstance(v, JSFunction): return "function"
     return "object"
@@ -171,6 +172,7 @@ def typeof(v):
 def strict_eq(a, b):
     if isinstance(a, float) and isinstance(b, float): return a == b
     if isinstance(a, bool) or isinstance(b, bool): return a is b
+    if isinstance(a, int) and isinstance(b, int): return a == b           # BigInt
     if isinstance(a, str) and isinstance(b, str): return a == b
     return a is b
 
@@ -302,6 +304,8 @@ def tokenize(src, fname="<js>"):
         m = NUM_RE.match(src, i)
         if m and (c.isdigit() or (c == "." and i + 1 < n and src[i + 1].isdigit())):
             t = m.group(0)
+            if m.end() < n and src[m.end()] == "n" and re.fullmatch(r"0[xX][0-9a-fA-F]+|\d+", t):      # BigInt literal: a Python int
+                toks.append(Tok("num", int(t, 16) if t[:2].lower() == "0x" else int(t), i, nl)); nl = False; i = m.end() + 1; continue
             toks.append(Tok("num", float(int(t, 16)) if t[:2].lower() == "0x" else float(t), i, nl)); nl = False; i = m.end(); continue
         m = ID_RE.match(src, i)
         if m:
@@ -407,7 +411,7 @@ class Parser:
                 if self.eat_kw("finally"): fin = self.block()
                 return ("try", blk, param, handler, fin)
             if v == "switch": return self.switch_stmt()
-            if v == "import" and not self.is_p(".", 1): return self.import_decl()
+            if v == "import" and not (self.is_p(".", 1) or self.is_p("(", 1)): return self.import_decl()
             if v == "export": return self.export_decl()
         e = self.expression(); self.semi(); return ("expr", e)
     def var_decl(self):
@@ -665,6 +669,8 @@ class Parser:
             if v == "class": self.i -= 1; return self.class_expr()
             if v == "import" and self.is_p(".") and self.peek(1).val == "meta":
                 self.next(); self.next(); return ("import_meta",)
+            if v == "import" and self.is_p("("):                                   # import(specifier): a promise of the module namespace
+                self.next(); e = self.assign(); self.expect_p(")"); return ("dyn_import", e)
             if v in CONTEXTUAL: return ("id", v)
         if k == "p":
             if v == "(":
@@ -1055,6 +1061,16 @@ class Interp:
                     e = e.parent
                 raise JSThrow(make_error("ReferenceError", name + " is not defined"))
             return get
+        if k == "dyn_import":
+            spec = self.expr(node[1])
+            def dyn(env):
+                sp = to_str(spec(env))
+                if sp in interp.builtin_modules: ex = interp.builtin_modules[sp]
+                else:
+                    path = sp[7:] if sp.startswith("file://") else (sp if os.path.isabs(sp) else os.path.join(env.get("%dir"), sp))
+                    ex = interp.load_module(path)
+                return JSObject(PROMISE_PROTO, {"%state": "fulfilled", "%value": JSObject(OBJECT_PROTO, dict(ex))})
+            return dyn
         if k == "import_meta":
             return lambda env: JSObject(OBJECT_PROTO, {"url": "file://" + str(env.get("%file"))})
         if k == "this":
@@ -1345,18 +1361,27 @@ class Interp:
             def add(env):
                 x = a(env); y = b(env)
                 if x.__class__ is float and y.__class__ is float: return x + y
+                if x.__class__ is int or y.__class__ is int:                         # BigInt
+                    if x.__class__ is int and y.__class__ is int: return x + y
+                    raise JSThrow(make_error("TypeError", "Cannot mix BigInt and other types, use explicit conversions"))
                 return js_add(x, y)
             return add
         if op == "-":
             def sub(env):
                 x = a(env); y = b(env)
                 if x.__class__ is float and y.__class__ is float: return x - y
+                if x.__class__ is int or y.__class__ is int:                         # BigInt
+                    if x.__class__ is int and y.__class__ is int: return x - y
+                    raise JSThrow(make_error("TypeError", "Cannot mix BigInt and other types, use explicit conversions"))
                 return to_num(x) - to_num(y)
             return sub
         if op == "*":
             def mul(env):
                 x = a(env); y = b(env)
                 if x.__class__ is float and y.__class__ is float: return x * y
+                if x.__class__ is int or y.__class__ is int:                         # BigInt
+                    if x.__class__ is int and y.__class__ is int: return x * y
+                    raise JSThrow(make_error("TypeError", "Cannot mix BigInt and other types, use explicit conversions"))
                 return to_num(x) * to_num(y)
             return mul
         if op == "/":
@@ -1394,7 +1419,15 @@ class Interp:
                 return ob.has(prop_key(key))
             return isin
         f = BINOPS[op]
-        return lambda env: f(a(env), b(env))
+        g = BIGINT_OPS.get(op)
+        def binop(env):
+            x = a(env); y = b(env)
+            if x.__class__ is int or y.__class__ is int:                  # BigInt (bool is its own class)
+                if not (x.__class__ is int and y.__class__ is int) or g is None:
+                    raise JSThrow(make_error("TypeError", "Cannot mix BigInt and other types, use explicit conversions"))
+                return g(x, y)
+            return f(x, y)
+        return binop
     def compile_class(self, node):
         _, name, sup, members = node
         sup_e = self.expr(sup) if sup is not None else None
@@ -1513,6 +1546,11 @@ BINOPS = {
 }
 
 
+BIGINT_OPS = {"+": lambda x, y: x + y, "-": lambda x, y: x - y, "*": lambda x, y: x * y, "&": lambda x, y: x & y, "|": lambda x, y: x | y, "^": lambda x, y: x ^ y,
+              "<<": lambda x, y: x << y, ">>": lambda x, y: x >> y, "==": lambda x, y: x == y, "!=": lambda x, y: x != y,
+              "<": lambda x, y: x < y, ">": lambda x, y: x > y, "<=": lambda x, y: x <= y, ">=": lambda x, y: x >= y}
+
+
 # ------------------------------------------------------------------------------------------------ globals / built-ins
 def py_to_js(v):
     """JSON-like Python data -> JS values"""
@@ -1606,6 +1644,13 @@ def install_globals(interp):
         return float(int(m.group(0))) if m else math.nan
     g["parseInt"] = native(parse_int, "parseInt")
     g["Number"] = native(lambda t, a: to_num(a[0]) if a else 0.0, "Number")
+    def bigint(t, a):
+        v = a[0] if a else UNDEF
+        if v.__class__ is int: return v
+        x = to_num(v)
+        if x != x or x in (math.inf, -math.inf) or x != math.floor(x): raise JSThrow(make_error("RangeError", "The number cannot be converted to a BigInt because it is not an integer"))
+        return int(x)
+    g["BigInt"] = native(bigint, "BigInt")
     g["Number"].props.update({"isFinite": native(lambda t, a: isinstance(a[0], float) and math.isfinite(a[0])), "isInteger": native(lambda t, a: isinstance(a[0], float) and math.isfinite(a[0]) and a[0] == int(a[0])),
                               "isNaN": native(lambda t, a: isinstance(a[0], float) and a[0] != a[0]), "EPSILON": 2.220446049250313e-16, "MAX_VALUE": 1.7976931348623157e308,
                               "MAX_SAFE_INTEGER": 9007199254740991.0, "POSITIVE_INFINITY": math.inf, "NEGATIVE_INFINITY": -math.inf})
@@ -1741,12 +1786,28 @@ def install_globals(interp):
         return p
     P = native(promise_ctor, "Promise"); P.props["prototype"] = PROMISE_PROTO
     P.props["resolve"] = native(lambda t, a: JSObject(PROMISE_PROTO, {"%state": "fulfilled", "%value": a[0] if a else UNDEF}))
-    def then(t, a):
-        if t.props.get("%state") == "rejected": return t
-        r = call(a[0], UNDEF, [t.props.get("%value", UNDEF)]) if a and isinstance(a[0], JSFunction) else t.props.get("%value", UNDEF)
+    def settle(fn, args):
+        """runs a reaction now (everything is already settled here): a returned promise is adopted, a throw rejects"""
+        try: r = call(fn, UNDEF, args)
+        except JSThrow as e: return JSObject(PROMISE_PROTO, {"%state": "rejected", "%value": e.value})
+        if isinstance(r, JSObject) and r.proto is PROMISE_PROTO: return r
         return JSObject(PROMISE_PROTO, {"%state": "fulfilled", "%value": r})
+    def then(t, a):
+        if t.props.get("%state") == "rejected":
+            return settle(a[1], [t.props.get("%value", UNDEF)]) if len(a) > 1 and isinstance(a[1], JSFunction) else t
+        if a and isinstance(a[0], JSFunction): return settle(a[0], [t.props.get("%value", UNDEF)])
+        return t
+    def catch(t, a):
+        if t.props.get("%state") == "rejected" and a and isinstance(a[0], JSFunction): return settle(a[0], [t.props.get("%value", UNDEF)])
+        return t
+    def fin(t, a):
+        if a and isinstance(a[0], JSFunction):
+            r = settle(a[0], [])
+            if r.props.get("%state") == "rejected": return r
+        return t
     PROMISE_PROTO.props["then"] = native(then, "then")
-    PROMISE_PROTO.props["catch"] = native(lambda t, a: t, "catch")
+    PROMISE_PROTO.props["catch"] = native(catch, "catch")
+    PROMISE_PROTO.props["finally"] = native(fin, "finally")
     g["Promise"] = P
     def set_timeout(t, a): call(a[0], UNDEF, list(a[2:])); return 0.0
     g["setTimeout"] = native(set_timeout, "setTimeout"); g["requestAnimationFrame"] = native(set_timeout, "requestAnimationFrame")

@@ -80,6 +80,10 @@ CASES = [
     ("let n = 0; const id = setInterval(() => { n++; }, 50); clearInterval(id); let out = [typeof id, n];", ["number", 0]),     # intervals are ticked by the host only
     ("const o = { solid: 1, hdri: 2 }; let out = [o['solid'] ?? 0, o['x'] ?? 0, { a: 1 }['a'], Array.from({ length: 3 }, (_, i) => i * 2)];", [1, 0, 1, [0, 2, 4]]),
     ("globalThis.zz = 5; let out = [zz, globalThis.Math === Math, globalThis.nope?.x, typeof globalThis.setInterval];", [5, True, None, "function"]),
+    # BigInt (baseline/run_ref.mjs computes Philox's 32 x 32 -> 64-bit products with it), import(), promise reactions
+    ("const p = 0xD2511F53n * BigInt(4000000000); let out = [Number(p >> 32n), Number(p & 0xFFFFFFFFn), typeof p, 7n === 7n, (Number(p >> 32n) ^ 5) >>> 0];", [3286201315, 4002805760, "bigint", True, 3286201318]),
+    ("let out; try { out = 1n + 1; } catch (e) { out = e.name; }", "TypeError"),
+    ("let out = []; Promise.resolve(1).then(v => { out.push(v); return Promise.resolve(2); }).then(v => out.push(v)).finally(() => out.push('f')); new Promise((_, rej) => rej(3)).catch(v => out.push(v));", [1, 2, "f", 3]),
     # async / await over immediately resolved promises (the reference yields with setTimeout between rows)
     ("let out = 0; async function r() { await new Promise(res => setTimeout(res, 1)); out = 7; return 3; } r();", 7.0),
 ]
