@@ -30,7 +30,6 @@ def gen_case(r, k):
 
 def run(seed, n, ref="/root/reference", verbose=False, emit=None):
     import numpy as np
-    import minijs as J
     import make_fixtures_minijs as M
     from test_reference_pin import oracle_render
     sys.setrecursionlimit(20000)

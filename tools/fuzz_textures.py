@@ -14,7 +14,6 @@ for p in (ROOT, os.path.join(ROOT, "baseline")):
 
 def run(seed, n, ref="/root/reference", points=40, verbose=False):
     import numpy as np
-    import minijs as J
     import make_fixtures_minijs as M
     import make_texture_fixtures_minijs as T
     from oracle.oracle import OracleRayTracer
