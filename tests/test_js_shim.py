@@ -347,3 +347,28 @@ def test_shim_flattening_on_random_scenes(addon):
         host.finalize_external(rt.get("_brt"))
         n += 1
     assert n >= 100
+
+
+@pytest.mark.gpu
+def test_shim_render_over_two_gpus(addon):
+    """installGpuRender(RayTracer, { devices: [0, 1] }): ONE render() call of the JS shim, the samples split over two GPUs inside
+    libbrt (brt_create_multi) — the image is the single-GPU image up to the fp32 order of the two partial sums (<= 1 LSB)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    W, H, spp, depth, seed = 160, 100, 16, 6, 5
+    py = brt.RayTracer(W, H, seed=seed + 1)
+    assert py.loadFromJSON(open(os.path.join(GOLDEN, "sample_mesh.json")).read())
+    py.updateRenderSettings(dict(samples=spp, maxBounces=depth))
+    want = py.render()
+    blits, progress = [], []
+    interp, host, rt = shim_raytracer(addon, describe(py), W, H, {"devices": [0, 1], "seed": seed}, blits)
+    rt.set("samples", float(spp)); rt.set("maxBounces", float(depth))
+    interp.call(rt.get("render"), rt, [J.native(lambda t, a: progress.append(a[0]))])
+    assert not host.log, host.log
+    got = np.asarray(rt.get("imageData").get("data").items, np.float64).astype(np.uint8).reshape(H, W, 4)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01 and progress[-1] == 1.0
+    stats = interp.call(interp.builtin_modules["node:module"]["createRequire"].native(None, [""]).native(None, ["./brt_addon.node"]).get("stats"), J.UNDEF, [rt.get("_brt")])
+    assert stats.get("devices") == 2.0
+    host.finalize_external(rt.get("_brt")); py.close()
