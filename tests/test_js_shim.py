@@ -360,10 +360,12 @@ def test_shim_render_over_two_gpus(addon):
     py = brt.RayTracer(W, H, seed=seed + 1)
     assert py.loadFromJSON(open(os.path.join(GOLDEN, "sample_mesh.json")).read())
     py.updateRenderSettings(dict(samples=spp, maxBounces=depth))
+    py.updateBackground("hdri", 1.2)                                    # the mock world starts from its own default background: set it on both sides
     want = py.render()
     blits, progress = [], []
     interp, host, rt = shim_raytracer(addon, describe(py), W, H, {"devices": [0, 1], "seed": seed}, blits)
     rt.set("samples", float(spp)); rt.set("maxBounces", float(depth))
+    interp.call(rt.get("updateBackground"), rt, ["hdri", 1.2])
     interp.call(rt.get("render"), rt, [J.native(lambda t, a: progress.append(a[0]))])
     assert not host.log, host.log
     got = np.asarray(rt.get("imageData").get("data").items, np.float64).astype(np.uint8).reshape(H, W, 4)
